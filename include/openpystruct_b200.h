@@ -1,0 +1,142 @@
+/*
+ * openpystruct_b200 -- C ABI of the B200-native beam moment-of-inertia optimiser.
+ *
+ * This is the drop-in boundary for ONE hot path of dsmyl6/OpenPyStruct: the per-sample optimisation
+ * loop of the training-data generators.  Each entry point states the reference interface it replaces
+ * (file:line into the reference repository):
+ *
+ *   generate_sample()'s epoch loop      OpenPyStruct_BeamOpt_training_SingleCore.py:163-232
+ *                                       OpenPyStruct_BeamOpt_training_MultiCore.py:165-223
+ *                                       OpenPyStruct_BeamOpt_training_GPU.py:173-251
+ *                                       OpenPyStruct_BeamOpt.py:180-237
+ *   which today crosses into native code through ~520 OpenSeesPy calls per epoch
+ *   (setup_model SingleCore:89-124, ops.analyze :182, ops.eleResponse :189-190, ops.nodeDisp :224-232)
+ *   and ~25 eager torch ops (loss :195-199, backward :202, Adam :203, ExponentialLR :204, clamp :208).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all arrays contiguous, row-major, BEAM-MAJOR;
+ *   - every buffer is caller-owned; the library never allocates device memory in the *_launch calls;
+ *   - *_launch calls are stream-ordered, re-entrant and never synchronise the device;
+ *   - return value: 0 ok, <0 invalid argument (OPS_E_*), >0 a cudaError_t value;
+ *   - per-beam numerical failure (non-SPD pivot / non-finite result; the reference's
+ *     `analyze() != 0 -> return None`, MultiCore:184-186) is reported in status[b], not as an error;
+ *   - there is NO CPU implementation behind this ABI: without a CUDA device every compute entry fails.
+ */
+#ifndef OPENPYSTRUCT_B200_H
+#define OPENPYSTRUCT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPS_E_BADARG   (-1)   /* null pointer, non-positive size, struct_size mismatch */
+#define OPS_E_UNSUPP   (-2)   /* configuration outside what the kernels implement */
+#define OPS_E_WORKSPACE (-3)  /* workspace too small */
+
+/* Module-level constants of the reference generators (SingleCore:20-49, MultiCore:20-52, GPU:21-56,
+ * BeamOpt:24-48) plus the literals of the loss (SingleCore:195-196) and torch's Adam defaults. */
+typedef struct OpsBeamOptParams {
+    int32_t struct_size;     /* sizeof(OpsBeamOptParams) -- ABI guard */
+    int32_t num_nodes;       /* num_nodes (101); elements n = num_nodes - 1 */
+    int32_t num_cases;       /* load cases sharing one I vector; the reference has 1 */
+    int32_t max_forces;      /* row width of force_nodes / force_vals (M_forces_max = 4; BeamOpt uses 5) */
+    int32_t max_epochs;      /* max_e (600; BeamOpt 1000) */
+    int32_t patience;        /* SC 5, MC 10 (def default shadows the constant), GPU 100, BeamOpt 10 */
+    int32_t early_stop;      /* 1 = reference behaviour; 0 = run exactly max_epochs (benchmark mode) */
+    int32_t zero_last_node;  /* 1 = MultiCore:222-223 emits 0.0 for the last node's uy / theta */
+    double E;                /* 200e9 */
+    double G;                /* E / (2 (1 + nu)) */
+    double udl;              /* uniform_udl (-1000; BeamOpt -5000), applied to every element */
+    double I0;               /* I_0 = 0.5 */
+    double lr;               /* 0.01 */
+    double gamma;            /* 0.98 (ExponentialLR) */
+    double alpha_moment;     /* 1e-2 */
+    double alpha_shear;      /* 1e-2 */
+    double tolerance;        /* 5e-3 (GPU / BeamOpt scripts: 1e-2) */
+    double shear_k;          /* 0.03  : A_approx = 0.03 * I**0.5      (SingleCore:196) */
+    double bending_eps;      /* 1e-6  : 2 E I + 1e-6                  (SingleCore:195) */
+    double clamp_min;        /* 1e-8  : I_tensor.clamp_(min=1e-8)     (SingleCore:208) */
+    double beta1, beta2, adam_eps;   /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 (SingleCore:166) */
+} OpsBeamOptParams;
+
+/* Library identification: "openpystruct_b200 <semver> sm_100a". */
+const char *ops_beamopt_version(void);
+
+/* Number of CUDA devices visible to the library (0 when there is none; compute entries then fail). */
+int ops_device_count(void);
+
+/* Makes `device` current for the calling thread (cudaSetDevice); the *_launch entries run on the
+ * current device, which must be the one that owns the buffers and the stream. */
+int ops_set_device(int device);
+
+/*
+ * Per-epoch Adam scalars.  torch computes bias corrections, the decayed learning rate
+ * (ExponentialLR, lr_t = lr_{t-1} * gamma) and step_size in Python doubles and rounds them to fp32
+ * when they meet the fp32 parameter tensor (torch/optim/adam.py:_single_tensor_adam); the kernel
+ * must see bit-identical values, so they are produced on the host in double.
+ * host_table receives 2*max_epochs floats: [-(lr_t/bc1_t), sqrt(bc2_t)] for t = 1..max_epochs.
+ * Replaces: optimizer/scheduler construction SingleCore:166-167 and scheduler.step() :204.
+ */
+int ops_beamopt_fill_schedule(const OpsBeamOptParams *p, float *host_table);
+
+/* Bytes of device scratch ops_beamopt_launch needs for B beams on the current device. */
+size_t ops_beamopt_workspace_bytes(const OpsBeamOptParams *p, int64_t B);
+
+/*
+ * The fused optimisation loop for B independent beams (device pointers).
+ *
+ * Inputs
+ *   fixed_uy     u8 [B][num_nodes]                1 = uy constrained (pin at node 0 is implied and
+ *                                                 forced; rollers: ops.fix(node,0,1,0) SingleCore:101-102)
+ *   force_nodes  i32[B][num_cases][max_forces]    0-based node index of each point load, <0 = unused
+ *   force_vals   f64[B][num_cases][max_forces]    ops.load(node, 0.0, F, 0.0) SingleCore:112-113
+ *   L            f64[B]                           beam length; node_positions = linspace(0, L, num_nodes)
+ *   d_schedule   f32[2*max_epochs]                ops_beamopt_fill_schedule() copied to the device
+ * Outputs (the tensors behind generate_sample's record, SingleCore:235-249)
+ *   I_values     f32[B][n]                        optimised inertias AFTER the last Adam step + clamp
+ *   deflections  f64[B][num_cases][num_nodes]     nodeDisp(i,2) of the LAST ANALYSED model
+ *   rotations    f64[B][num_cases][num_nodes]     nodeDisp(i,3)        "
+ *   shear        f32[B][num_cases][n]             eleResponse(e,'forces')[1] cast to fp32   "
+ *   moment       f32[B][num_cases][n]             eleResponse(e,'forces')[2] cast to fp32   "
+ *   epochs       i32[B]                           iterations executed (early stop SingleCore:211-219)
+ *   loss         f32[B]                           total_loss of the last iteration
+ *   status       i32[B]                           0 ok, 1 = factorisation/solve failed (sample to be dropped)
+ */
+int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
+                       const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                       const double *L, const float *d_schedule,
+                       float *I_values, double *deflections, double *rotations, float *shear,
+                       float *moment, int32_t *epochs, float *loss, int32_t *status,
+                       void *d_workspace, size_t workspace_bytes, void *cuda_stream);
+
+/*
+ * One static solve per beam for given inertias, everything in FP64 (no optimiser): the
+ * setup_model + analyze + eleResponse + nodeDisp sequence (SingleCore:176-190, 224-232) in isolation.
+ * I_f64[B][n]; single load case (force arrays [B][max_forces]); outputs f64 [B][num_nodes] / [B][n].
+ */
+int ops_beamsolve_launch(const OpsBeamOptParams *p, int64_t B,
+                         const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                         const double *L, const double *I_f64,
+                         double *deflections, double *rotations, double *shear, double *moment,
+                         int32_t *status, void *cuda_stream);
+
+/*
+ * Host-buffer convenience around ops_beamopt_launch for callers that are not torch (ctypes / cffi
+ * from the reference's scripts): allocates device buffers, copies inputs H2D, runs, copies every
+ * output D2H, synchronises, frees.  Same arrays as above but HOST pointers; `device` is the CUDA
+ * ordinal.  elapsed_ms (optional) receives the device time of the launch alone.
+ */
+int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
+                         const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                         const double *L,
+                         float *I_values, double *deflections, double *rotations, float *shear,
+                         float *moment, int32_t *epochs, float *loss, int32_t *status,
+                         int device, float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENPYSTRUCT_B200_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of include/openpystruct_b200.h.  There is no CPU implementation behind it:
+a missing library or a missing CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB_PATH
+from .params import BeamOptParams
+
+_lib = None
+
+EXPORTS = (
+    "ops_beamopt_version", "ops_device_count", "ops_set_device", "ops_beamopt_fill_schedule",
+    "ops_beamopt_workspace_bytes", "ops_beamopt_launch", "ops_beamsolve_launch", "ops_beamopt_run_host",
+)
+
+
+class OpsBeamOptParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("num_nodes", C.c_int32), ("num_cases", C.c_int32),
+        ("max_forces", C.c_int32), ("max_epochs", C.c_int32), ("patience", C.c_int32),
+        ("early_stop", C.c_int32), ("zero_last_node", C.c_int32),
+        ("E", C.c_double), ("G", C.c_double), ("udl", C.c_double), ("I0", C.c_double),
+        ("lr", C.c_double), ("gamma", C.c_double), ("alpha_moment", C.c_double),
+        ("alpha_shear", C.c_double), ("tolerance", C.c_double), ("shear_k", C.c_double),
+        ("bending_eps", C.c_double), ("clamp_min", C.c_double), ("beta1", C.c_double),
+        ("beta2", C.c_double), ("adam_eps", C.c_double),
+    ]
+
+
+class CudaLibraryError(RuntimeError):
+    pass
+
+
+def to_c_params(p: BeamOptParams) -> OpsBeamOptParams:
+    return OpsBeamOptParams(
+        C.sizeof(OpsBeamOptParams), p.num_nodes, p.num_cases, p.max_forces, p.max_e, p.patience,
+        int(p.early_stop), int(p.zero_last_node), p.E, p.G, p.uniform_udl, p.I_0, p.lr, p.gamma,
+        p.alpha_moment, p.alpha_shear, p.tolerance, p.shear_k, p.bending_eps, p.clamp_min,
+        p.beta1, p.beta2, p.adam_eps)
+
+
+def lib():
+    """The loaded CUDA library; raises CudaLibraryError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CudaLibraryError(
+                f"{LIB_PATH} is missing: build it with `python -m openpystruct_b200.build` "
+                "(there is no CPU fallback for this path)")
+        L = C.CDLL(LIB_PATH)
+        L.ops_beamopt_version.restype = C.c_char_p
+        L.ops_device_count.restype = C.c_int
+        L.ops_set_device.argtypes = [C.c_int]
+        L.ops_beamopt_fill_schedule.argtypes = [C.POINTER(OpsBeamOptParams), C.c_void_p]
+        L.ops_beamopt_workspace_bytes.restype = C.c_size_t
+        L.ops_beamopt_workspace_bytes.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64]
+        L.ops_beamopt_launch.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 13 + \
+            [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ops_beamsolve_launch.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 10 + \
+            [C.c_void_p]
+        L.ops_beamopt_run_host.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 12 + \
+            [C.c_int, C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    names = {-1: "OPS_E_BADARG", -2: "OPS_E_UNSUPP", -3: "OPS_E_WORKSPACE"}
+    if rc < 0:
+        raise CudaLibraryError(f"{what}: {names.get(rc, rc)}")
+    raise CudaLibraryError(f"{what}: cudaError {rc}")
+
+
+def version() -> str:
+    return lib().ops_beamopt_version().decode()
+
+
+def fill_schedule(p: BeamOptParams) -> np.ndarray:
+    """[max_e, 2] fp32 table of (-(lr_t / bias_correction1), sqrt(bias_correction2))."""
+    cp = to_c_params(p)
+    table = np.zeros((max(p.max_e, 1), 2), np.float32)
+    check(lib().ops_beamopt_fill_schedule(C.byref(cp), table.ctypes.data), "ops_beamopt_fill_schedule")
+    return table
+
+
+def run_host(p: BeamOptParams, fixed_uy, force_nodes, force_vals, L, device: int = 0) -> dict:
+    """ops_beamopt_run_host: host numpy buffers in, host numpy buffers out (H2D/D2H inside)."""
+    L = np.ascontiguousarray(L, np.float64).reshape(-1)
+    B, nn, Cc, F = L.shape[0], p.num_nodes, p.num_cases, p.max_forces
+    n = nn - 1
+    fixed_uy = np.ascontiguousarray(fixed_uy, np.uint8).reshape(B, nn)
+    force_nodes = np.ascontiguousarray(force_nodes, np.int32).reshape(B, Cc, F)
+    force_vals = np.ascontiguousarray(force_vals, np.float64).reshape(B, Cc, F)
+    out = {
+        "I": np.empty((B, n), np.float32), "defl": np.empty((B, Cc, nn)), "rot": np.empty((B, Cc, nn)),
+        "shear": np.empty((B, Cc, n), np.float32), "moment": np.empty((B, Cc, n), np.float32),
+        "epochs": np.empty(B, np.int32), "loss": np.empty(B, np.float32), "status": np.empty(B, np.int32),
+    }
+    ms = C.c_float(0.0)
+    cp = to_c_params(p)
+    rc = lib().ops_beamopt_run_host(
+        C.byref(cp), B, fixed_uy.ctypes.data, force_nodes.ctypes.data, force_vals.ctypes.data,
+        L.ctypes.data, out["I"].ctypes.data, out["defl"].ctypes.data, out["rot"].ctypes.data,
+        out["shear"].ctypes.data, out["moment"].ctypes.data, out["epochs"].ctypes.data,
+        out["loss"].ctypes.data, out["status"].ctypes.data, device, C.byref(ms))
+    check(rc, "ops_beamopt_run_host")
+    out["kernel_ms"] = float(ms.value)
+    return out

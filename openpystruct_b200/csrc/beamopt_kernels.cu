@@ -1,0 +1,513 @@
+// sm_100a kernels + C ABI (include/openpystruct_b200.h) of the beam moment-of-inertia optimiser.
+//
+// Execution model: persistent grid, ONE THREAD PER BEAM.  A lane that finishes its beam (early stop,
+// SingleCore:211-219) pulls the next beam index from a global counter, so ragged stopping does not
+// idle the warp.  The per-beam factor (5 doubles per node) and the fp32 optimiser state (I, m, v)
+// live in shared memory laid out [slot][thread]; nothing but the beam's inputs (read once) and its
+// results (written once) crosses HBM.  For discretisations whose state does not fit in shared
+// memory the same code runs on a global-memory scratch (`workspace`) laid out the same way.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see beamopt_core.cuh).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/openpystruct_b200.h"
+#include "beamopt_core.cuh"
+
+#define OPS_VERSION "openpystruct_b200 0.1.0 sm_100a"
+
+namespace ops {
+
+struct OptPtrs {
+    const uint8_t *fixed_uy;
+    const int32_t *force_nodes;
+    const double *force_vals;
+    const double *L;
+    const float *sched;
+    float *I_values;
+    double *defl, *rot;
+    float *shear, *moment;
+    int32_t *epochs;
+    float *loss;
+    int32_t *status;
+    unsigned long long *counter;
+    double *ws_d;      // global scratch (only when !SMEM)
+    float *ws_f;
+    uint32_t *ws_mask;
+};
+
+// fixed-uy bitmask words per beam, laid out [word][thread]
+struct MaskStore {
+    uint32_t *w;
+    long stride;
+    OPS_HD bool operator()(int i) const
+    {
+        return (w[(long)(i >> 5) * stride] >> (i & 31)) & 1u;
+    }
+};
+
+template <int MAXF, bool SMEM>
+__global__ void __launch_bounds__(128) beamopt_kernel(const BeamConsts k, const long long B, const OptPtrs p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    const int n = k.n, nn = k.nn;
+    const int mask_words = (nn + 31) >> 5;
+
+    BeamStore st;
+    MaskStore fixed;
+    if (SMEM) {
+        double *sd = reinterpret_cast<double *>(smem_raw);
+        float *sf = reinterpret_cast<float *>(sd + (size_t)5 * nn * T);
+        uint32_t *sm = reinterpret_cast<uint32_t *>(sf + (size_t)3 * n * T);
+        st.d = sd + threadIdx.x;
+        st.f = sf + threadIdx.x;
+        st.stride = T;
+        fixed.w = sm + threadIdx.x;
+        fixed.stride = T;
+    } else {
+        const long total = (long)gridDim.x * T;
+        const long gtid = (long)blockIdx.x * T + threadIdx.x;
+        st.d = p.ws_d + gtid;
+        st.f = p.ws_f + gtid;
+        st.stride = total;
+        fixed.w = p.ws_mask + gtid;
+        fixed.stride = total;
+    }
+
+    BeamInputs<MAXF> in;
+    long long b = -1;
+    bool have = false, exhausted = false;
+    int t = 0, counter = 0, bad = 0;
+    double best = INFINITY;
+    float lossf = NAN;
+
+    while (true) {
+        if (!have && !exhausted) {
+            b = (long long)atomicAdd(p.counter, 1ULL);
+            if (b < B) {
+                have = true;
+                t = 0; counter = 0; bad = 0; best = INFINITY; lossf = NAN;
+                beam_geometry<MAXF>(k, p.L[b], in);
+#pragma unroll
+                for (int j = 0; j < MAXF; ++j) {
+                    const bool on = j < k.max_forces;
+                    in.fnode[j] = on ? p.force_nodes[b * k.max_forces + j] : -1;
+                    in.fval[j] = on ? p.force_vals[b * k.max_forces + j] : 0.0;
+                }
+                for (int w = 0; w < mask_words; ++w) {
+                    uint32_t bits = 0;
+                    for (int i = 0; i < 32 && 32 * w + i < nn; ++i)
+                        bits |= (p.fixed_uy[b * nn + 32 * w + i] ? 1u : 0u) << i;
+                    fixed.w[(long)w * fixed.stride] = bits;
+                }
+                for (int e = 0; e < n; ++e) {
+                    st.F(e) = k.I0f;
+                    st.F(n + e) = 0.0f;
+                    st.F(2 * n + e) = 0.0f;
+                }
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            int rc = 0;
+            bool done = (k.max_epochs <= 0);
+            if (!done) {
+                const float neg_step = __ldg(p.sched + 2 * t);
+                const float bc2_sqrt = __ldg(p.sched + 2 * t + 1);
+                lossf = beam_iteration<MAXF>(k, in, st, fixed, neg_step, bc2_sqrt, &rc);
+                ++t;
+                if (rc) { bad = 1; done = true; }
+                if (k.early_stop) {
+                    const double l = (double)lossf;
+                    if (l < best - k.tol) { best = l; counter = 0; } else { ++counter; }
+                    if (counter >= k.patience) done = true;
+                }
+                if (t >= k.max_epochs) done = true;
+            }
+            if (done) {
+                for (int e = 0; e < n; ++e) {
+                    p.I_values[b * n + e] = st.F(e);
+                    const float *mv = st.pairf(5 * e);
+                    p.moment[b * n + e] = t > 0 ? mv[0] : 0.0f;
+                    p.shear[b * n + e] = t > 0 ? mv[1] : 0.0f;
+                }
+                for (int i = 0; i < nn; ++i) {
+                    const bool z = (t == 0) || (k.zero_last_node && i == nn - 1);
+                    p.defl[b * nn + i] = z ? 0.0 : st.D(5 * i + 3);
+                    p.rot[b * nn + i] = z ? 0.0 : st.D(5 * i + 4);
+                }
+                p.epochs[b] = t;
+                p.loss[b] = lossf;
+                p.status[b] = bad;
+                have = false;
+            }
+        }
+    }
+}
+
+struct SolvePtrs {
+    const uint8_t *fixed_uy;
+    const int32_t *force_nodes;
+    const double *force_vals;
+    const double *L;
+    const double *I;
+    double *defl, *rot, *shear, *moment;
+    int32_t *status;
+};
+
+// One solve per beam, thread per beam, factor in shared memory [slot][thread].
+template <int MAXF>
+__global__ void __launch_bounds__(128) beamsolve_kernel(const BeamConsts k, const long long B, const SolvePtrs p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    const int n = k.n, nn = k.nn;
+    const long long b = (long long)blockIdx.x * T + threadIdx.x;
+    if (b >= B) return;
+    BeamStore st;
+    st.d = reinterpret_cast<double *>(smem_raw) + threadIdx.x;
+    st.f = nullptr;
+    st.stride = T;
+    BeamInputs<MAXF> in;
+    beam_geometry<MAXF>(k, p.L[b], in);
+#pragma unroll
+    for (int j = 0; j < MAXF; ++j) {
+        const bool on = j < k.max_forces;
+        in.fnode[j] = on ? p.force_nodes[b * k.max_forces + j] : -1;
+        in.fval[j] = on ? p.force_vals[b * k.max_forces + j] : 0.0;
+    }
+    const uint8_t *fx = p.fixed_uy + b * nn;
+    const double *Ib = p.I + b * n;
+    auto fixed = [&](int i) { return fx[i] != 0; };
+    auto inertia = [&](int e) { return Ib[e]; };
+    int rc = factor_forward<MAXF>(k, in, st, fixed, inertia);
+    rc |= solve_backward<MAXF>(k, in, st, fixed, inertia, [&](int e, double V, double M) {
+        p.shear[b * n + e] = V;
+        p.moment[b * n + e] = M;
+    });
+    for (int i = 0; i < nn; ++i) {
+        p.defl[b * nn + i] = st.D(5 * i + 3);
+        p.rot[b * nn + i] = st.D(5 * i + 4);
+    }
+    p.status[b] = rc;
+}
+
+static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
+{
+    if (!p || p->struct_size != (int32_t)sizeof(OpsBeamOptParams)) return OPS_E_BADARG;
+    if (p->num_nodes < 2 || p->num_cases < 1 || p->max_forces < 0 || p->max_epochs < 0) return OPS_E_BADARG;
+    if (p->num_cases != 1) return OPS_E_UNSUPP;
+    if (p->max_forces > 8) return OPS_E_UNSUPP;
+    k->nn = p->num_nodes;
+    k->n = p->num_nodes - 1;
+    k->max_forces = p->max_forces;
+    k->max_epochs = p->max_epochs;
+    k->patience = p->patience;
+    k->early_stop = p->early_stop;
+    k->zero_last_node = p->zero_last_node;
+    k->E = p->E;
+    k->udl = p->udl;
+    k->tol = p->tolerance;
+    k->I0f = (float)p->I0;
+    k->E2 = (float)(2.0 * p->E);
+    k->Gf = (float)p->G;
+    k->kf = (float)p->shear_k;
+    k->am = (float)p->alpha_moment;
+    k->as_ = (float)p->alpha_shear;
+    k->epsf = (float)p->bending_eps;
+    k->clampf = (float)p->clamp_min;
+    k->w1 = (float)(1.0 - p->beta1);
+    k->b2f = (float)p->beta2;
+    k->omb2f = (float)(1.0 - p->beta2);
+    k->adam_epsf = (float)p->adam_eps;
+    return 0;
+}
+
+struct LaunchPlan {
+    bool smem;
+    int threads;         // per CTA
+    int blocks;
+    size_t smem_bytes;
+    size_t ws_d_bytes, ws_f_bytes, ws_mask_bytes;   // global scratch (0 when smem)
+};
+
+static size_t per_beam_bytes(int nn)
+{
+    const int n = nn - 1;
+    return (size_t)5 * nn * 8 + (size_t)3 * n * 4 + (size_t)((nn + 31) / 32) * 4;
+}
+
+static int plan_launch(const BeamConsts &k, int64_t B, LaunchPlan *pl)
+{
+    int dev = 0, sms = 0, smem_optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return (int)e;
+    const size_t pb = per_beam_bytes(k.nn);
+    memset(pl, 0, sizeof *pl);
+    // experiment knobs (profiling only): OPS_BEAMOPT_GLOBAL=1 forces the global-scratch variant,
+    // OPS_BEAMOPT_CTAS_PER_SM sets its residency.
+    const char *force_global = getenv("OPS_BEAMOPT_GLOBAL");
+    const char *ctas_env = getenv("OPS_BEAMOPT_CTAS_PER_SM");
+    const int ctas_per_sm = ctas_env ? atoi(ctas_env) : 4;
+    if (32 * pb <= (size_t)smem_optin && !(force_global && force_global[0] == '1')) {
+        pl->smem = true;
+        pl->threads = 32;
+        pl->smem_bytes = 32 * pb;
+        int per_sm = (int)((size_t)smem_optin / pl->smem_bytes);
+        if (per_sm < 1) per_sm = 1;
+        long want = (long)((B + 31) / 32);
+        long cap = (long)sms * per_sm;
+        pl->blocks = (int)(want < cap ? want : cap);
+    } else {
+        pl->smem = false;
+        pl->threads = 64;
+        long want = (long)((B + 63) / 64);
+        long cap = (long)sms * (ctas_per_sm > 0 ? ctas_per_sm : 4);
+        pl->blocks = (int)(want < cap ? want : cap);
+        const size_t total = (size_t)pl->blocks * pl->threads;
+        pl->ws_d_bytes = total * 5 * k.nn * 8;
+        pl->ws_f_bytes = total * 3 * k.n * 4;
+        pl->ws_mask_bytes = total * ((k.nn + 31) / 32) * 4;
+    }
+    if (pl->blocks < 1) pl->blocks = 1;
+    return 0;
+}
+
+}  // namespace ops
+
+using namespace ops;
+
+extern "C" {
+
+const char *ops_beamopt_version(void) { return OPS_VERSION; }
+
+int ops_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ops_set_device(int device)
+{
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return 0;
+}
+
+int ops_beamopt_fill_schedule(const OpsBeamOptParams *p, float *host_table)
+{
+    if (!p || !host_table || p->struct_size != (int32_t)sizeof(OpsBeamOptParams)) return OPS_E_BADARG;
+    // torch/optim/adam.py (_single_tensor_adam) + lr_scheduler.ExponentialLR, all in double:
+    //   bias_correction1 = 1 - beta1**step ; bias_correction2 = 1 - beta2**step
+    //   step_size = lr / bias_correction1 ; bias_correction2_sqrt = bias_correction2**0.5
+    //   lr <- lr * gamma after every optimizer step
+    double lr = p->lr;
+    for (int t = 1; t <= p->max_epochs; ++t) {
+        const double bc1 = 1.0 - pow(p->beta1, (double)t);
+        const double bc2 = 1.0 - pow(p->beta2, (double)t);
+        host_table[2 * (t - 1)] = (float)(-(lr / bc1));
+        host_table[2 * (t - 1) + 1] = (float)pow(bc2, 0.5);
+        lr = lr * p->gamma;
+    }
+    return 0;
+}
+
+size_t ops_beamopt_workspace_bytes(const OpsBeamOptParams *p, int64_t B)
+{
+    BeamConsts k;
+    if (make_consts(p, &k) != 0 || B < 0) return 0;
+    LaunchPlan pl;
+    if (plan_launch(k, B, &pl) != 0) return 0;
+    return 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
+}
+
+int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
+                       const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                       const double *L, const float *d_schedule,
+                       float *I_values, double *deflections, double *rotations, float *shear,
+                       float *moment, int32_t *epochs, float *loss, int32_t *status,
+                       void *d_workspace, size_t workspace_bytes, void *cuda_stream)
+{
+    BeamConsts k;
+    int rc = make_consts(p, &k);
+    if (rc) return rc;
+    if (B < 0) return OPS_E_BADARG;
+    if (B == 0) return 0;
+    if (!fixed_uy || !L || !I_values || !deflections || !rotations || !shear || !moment || !epochs ||
+        !loss || !status || !d_workspace || (p->max_forces > 0 && (!force_nodes || !force_vals)) ||
+        (p->max_epochs > 0 && !d_schedule))
+        return OPS_E_BADARG;
+    LaunchPlan pl;
+    rc = plan_launch(k, B, &pl);
+    if (rc) return rc;
+    const size_t need = 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
+    if (workspace_bytes < need) return OPS_E_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+
+    unsigned char *ws = (unsigned char *)d_workspace;
+    OptPtrs q;
+    q.fixed_uy = fixed_uy; q.force_nodes = force_nodes; q.force_vals = force_vals; q.L = L;
+    q.sched = d_schedule; q.I_values = I_values; q.defl = deflections; q.rot = rotations;
+    q.shear = shear; q.moment = moment; q.epochs = epochs; q.loss = loss; q.status = status;
+    q.counter = (unsigned long long *)ws;
+    size_t off = 256;
+    q.ws_d = (double *)(ws + off); off += (pl.ws_d_bytes + 255) / 256 * 256;
+    q.ws_f = (float *)(ws + off);  off += (pl.ws_f_bytes + 255) / 256 * 256;
+    q.ws_mask = (uint32_t *)(ws + off);
+    cudaError_t e = cudaMemsetAsync(q.counter, 0, 256, stream);
+    if (e != cudaSuccess) return (int)e;
+
+    const int mf = p->max_forces <= 4 ? 4 : 8;
+#define OPS_LAUNCH(MAXF, SMEM)                                                                      \
+    do {                                                                                            \
+        auto kern = beamopt_kernel<MAXF, SMEM>;                                                     \
+        if (SMEM) {                                                                                 \
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                     (int)pl.smem_bytes);                                           \
+            if (e != cudaSuccess) return (int)e;                                                    \
+        }                                                                                           \
+        kern<<<pl.blocks, pl.threads, SMEM ? pl.smem_bytes : 0, stream>>>(k, (long long)B, q);      \
+    } while (0)
+    if (pl.smem) { if (mf == 4) OPS_LAUNCH(4, true); else OPS_LAUNCH(8, true); }
+    else         { if (mf == 4) OPS_LAUNCH(4, false); else OPS_LAUNCH(8, false); }
+#undef OPS_LAUNCH
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int ops_beamsolve_launch(const OpsBeamOptParams *p, int64_t B,
+                         const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                         const double *L, const double *I_f64,
+                         double *deflections, double *rotations, double *shear, double *moment,
+                         int32_t *status, void *cuda_stream)
+{
+    BeamConsts k;
+    int rc = make_consts(p, &k);
+    if (rc) return rc;
+    if (B < 0) return OPS_E_BADARG;
+    if (B == 0) return 0;
+    if (!fixed_uy || !L || !I_f64 || !deflections || !rotations || !shear || !moment || !status ||
+        (p->max_forces > 0 && (!force_nodes || !force_vals)))
+        return OPS_E_BADARG;
+    int dev = 0, smem_optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return (int)e;
+    const size_t pb = (size_t)5 * k.nn * 8;
+    int threads = 32;
+    while (threads > 1 && threads * pb > (size_t)smem_optin) threads >>= 1;
+    if (threads * pb > (size_t)smem_optin) return OPS_E_UNSUPP;
+    const size_t smem = threads * pb;
+    const int blocks = (int)((B + threads - 1) / threads);
+    SolvePtrs q;
+    q.fixed_uy = fixed_uy; q.force_nodes = force_nodes; q.force_vals = force_vals; q.L = L; q.I = I_f64;
+    q.defl = deflections; q.rot = rotations; q.shear = shear; q.moment = moment; q.status = status;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const int mf = p->max_forces <= 4 ? 4 : 8;
+    if (mf == 4) {
+        auto kern = beamsolve_kernel<4>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<blocks, threads, smem, stream>>>(k, (long long)B, q);
+    } else {
+        auto kern = beamsolve_kernel<8>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<blocks, threads, smem, stream>>>(k, (long long)B, q);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+#define OPS_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (int)e_; goto done; } } while (0)
+
+int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
+                         const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                         const double *L,
+                         float *I_values, double *deflections, double *rotations, float *shear,
+                         float *moment, int32_t *epochs, float *loss, int32_t *status,
+                         int device, float *elapsed_ms)
+{
+    BeamConsts k;
+    int rc = make_consts(p, &k);
+    if (rc) return rc;
+    if (B < 0) return OPS_E_BADARG;
+    if (B == 0) return 0;
+    if (!fixed_uy || !L || !I_values || !deflections || !rotations || !shear || !moment || !epochs ||
+        !loss || !status)
+        return OPS_E_BADARG;
+    const size_t nn = k.nn, n = k.n, C = 1, F = (size_t)p->max_forces;
+    const size_t sz_fixed = (size_t)B * nn, sz_fn = (size_t)B * C * F * 4, sz_fv = (size_t)B * C * F * 8;
+    const size_t sz_L = (size_t)B * 8, sz_sched = (size_t)(p->max_epochs > 0 ? p->max_epochs : 1) * 8;
+    const size_t sz_I = (size_t)B * n * 4, sz_u = (size_t)B * C * nn * 8, sz_s = (size_t)B * C * n * 4;
+    const size_t sz_i32 = (size_t)B * 4;
+    unsigned char *dbuf = nullptr;
+    float *sched_h = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t ws_bytes = 0, total = 0, off = 0;
+    size_t o_fixed, o_fn, o_fv, o_L, o_sched, o_I, o_defl, o_rot, o_sh, o_mo, o_ep, o_loss, o_st, o_ws;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    OPS_CUDA(cudaSetDevice(device));
+    ws_bytes = ops_beamopt_workspace_bytes(p, B);
+    if (ws_bytes == 0) { rc = OPS_E_BADARG; goto done; }
+    o_fixed = take(sz_fixed); o_fn = take(sz_fn); o_fv = take(sz_fv); o_L = take(sz_L); o_sched = take(sz_sched);
+    o_I = take(sz_I); o_defl = take(sz_u); o_rot = take(sz_u); o_sh = take(sz_s); o_mo = take(sz_s);
+    o_ep = take(sz_i32); o_loss = take(sz_i32); o_st = take(sz_i32); o_ws = take(ws_bytes);
+    total = off;
+    sched_h = (float *)malloc(sz_sched);
+    if (!sched_h) { rc = OPS_E_BADARG; goto done; }
+    ops_beamopt_fill_schedule(p, sched_h);
+    OPS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    OPS_CUDA(cudaEventCreate(&ev0));
+    OPS_CUDA(cudaEventCreate(&ev1));
+    OPS_CUDA(cudaMallocAsync((void **)&dbuf, total, stream));
+    OPS_CUDA(cudaMemcpyAsync(dbuf + o_fixed, fixed_uy, sz_fixed, cudaMemcpyHostToDevice, stream));
+    if (F > 0) {
+        OPS_CUDA(cudaMemcpyAsync(dbuf + o_fn, force_nodes, sz_fn, cudaMemcpyHostToDevice, stream));
+        OPS_CUDA(cudaMemcpyAsync(dbuf + o_fv, force_vals, sz_fv, cudaMemcpyHostToDevice, stream));
+    }
+    OPS_CUDA(cudaMemcpyAsync(dbuf + o_L, L, sz_L, cudaMemcpyHostToDevice, stream));
+    OPS_CUDA(cudaMemcpyAsync(dbuf + o_sched, sched_h, sz_sched, cudaMemcpyHostToDevice, stream));
+    OPS_CUDA(cudaEventRecord(ev0, stream));
+    rc = ops_beamopt_launch(p, B, dbuf + o_fixed, (const int32_t *)(dbuf + o_fn), (const double *)(dbuf + o_fv),
+                            (const double *)(dbuf + o_L), (const float *)(dbuf + o_sched),
+                            (float *)(dbuf + o_I), (double *)(dbuf + o_defl), (double *)(dbuf + o_rot),
+                            (float *)(dbuf + o_sh), (float *)(dbuf + o_mo), (int32_t *)(dbuf + o_ep),
+                            (float *)(dbuf + o_loss), (int32_t *)(dbuf + o_st), dbuf + o_ws, ws_bytes, stream);
+    if (rc) goto done;
+    OPS_CUDA(cudaEventRecord(ev1, stream));
+    OPS_CUDA(cudaMemcpyAsync(I_values, dbuf + o_I, sz_I, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaMemcpyAsync(deflections, dbuf + o_defl, sz_u, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaMemcpyAsync(rotations, dbuf + o_rot, sz_u, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaMemcpyAsync(shear, dbuf + o_sh, sz_s, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaMemcpyAsync(moment, dbuf + o_mo, sz_s, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaMemcpyAsync(epochs, dbuf + o_ep, sz_i32, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaMemcpyAsync(loss, dbuf + o_loss, sz_i32, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaMemcpyAsync(status, dbuf + o_st, sz_i32, cudaMemcpyDeviceToHost, stream));
+    OPS_CUDA(cudaStreamSynchronize(stream));
+    if (elapsed_ms) OPS_CUDA(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
+done:
+    if (dbuf && stream) { cudaFreeAsync(dbuf, stream); cudaStreamSynchronize(stream); }
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+    free(sched_h);
+    if (rc > 0) cudaGetLastError();
+    return rc;
+}
+
+}  // extern "C"

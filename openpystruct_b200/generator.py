@@ -1,0 +1,181 @@
+"""Host mirror of the reference generators' ``generate_sample`` / ``main``.
+
+Same entry-point name, argument meaning and record schema as the reference
+(``generate_sample(sample_idx, num_nodes, flag, L, node_positions, roller_nodes, available_nodes,
+patience[, device]) -> dict | None``, SingleCore:126-249 / MultiCore:130-240 / GPU:131-274; the
+13-key record SingleCore:235-249; dict-of-lists ``training_data`` + ``json.dump`` SingleCore:73-87,
+263-264), but the inner epoch loop runs as ONE CUDA launch over a whole batch of samples.
+
+What stays on the host, unchanged in behaviour: the sampling of supports and loads (``sampling``),
+the packing of the record, the JSON dump.  What moves to the GPU: everything between
+``I_tensor = torch.tensor([I_0] * num_elements ...)`` and the ``nodeDisp`` read-out.
+"""
+from __future__ import annotations
+
+import dataclasses
+import json
+import random
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops as _ops
+from . import sampling
+from .params import BeamOptParams
+
+TRAINING_DATA_KEYS = (
+    "roller_x_locations", "force_x_locations", "force_values", "I_values", "shear_forces",
+    "bending_moments", "node_positions", "roller_nodes", "force_nodes", "num_nodes", "L",
+    "rotations", "deflections",
+)
+
+
+@dataclasses.dataclass(frozen=True)
+class GeneratorConfig:
+    """Module-level constants of a generator script (SingleCore:20-49) that are not solver params."""
+    params: BeamOptParams = BeamOptParams()
+    L_max: float = 200.0
+    L_min: float = 15.0
+    N_rollers_max: int = 4
+    M_forces_max: int = 4
+    max_force: float = -355857
+    num_samples: int = 100000
+    random_bridge: int = 0           # flag
+    roller_nodes: Optional[tuple] = None    # default [10, 30, 70, 85, num_nodes - 1]
+    output_file: str = "training_data_PINN_mini.json"
+
+    @property
+    def min_force(self) -> float:
+        return self.max_force / 10
+
+    @staticmethod
+    def single_core() -> "GeneratorConfig":
+        return GeneratorConfig(params=BeamOptParams.for_script("SC"))
+
+    @staticmethod
+    def multi_core() -> "GeneratorConfig":
+        return GeneratorConfig(params=BeamOptParams.for_script("MC"))
+
+    @staticmethod
+    def gpu() -> "GeneratorConfig":
+        return GeneratorConfig(params=BeamOptParams.for_script("GPU"))
+
+
+def _require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("openpystruct_b200 runs the optimisation loop on a CUDA device only "
+                           "(no CPU fallback); got device=%r, cuda available=%s"
+                           % (device, torch.cuda.is_available()))
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device="cuda") -> dict:
+    """Pack sampled cases, copy them to the GPU, run the fused loop, bring the results back (numpy)."""
+    dev = _require_cuda(device)
+    fixed, fn, fv, L = sampling.pack_cases(params.num_nodes, params.max_forces, cases, params.num_cases)
+    t = lambda a: torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)   # noqa: E731
+    out = _ops.optimise_beams(params, t(fixed), t(fn), t(fv), t(L))
+    host = {k: v.cpu() for k, v in out.items()}
+    return {k: v.numpy() for k, v in host.items()}
+
+
+def make_records(params: BeamOptParams, cases: Sequence[sampling.Case], out: dict) -> List[Optional[dict]]:
+    """The 13-key records of SingleCore:235-249, one per (beam, load case); None where status != 0
+    (the MultiCore filter, MultiCore:184-186, 265)."""
+    C = params.num_cases
+    records: List[Optional[dict]] = []
+    for i, (L, rollers, force_nodes, force_values) in enumerate(cases):
+        b, c = divmod(i, C)
+        if out["status"][b] != 0:
+            records.append(None)
+            continue
+        rollers_b = cases[b * C][1]
+        L_b = cases[b * C][0]
+        node_positions = np.linspace(0, L_b, params.num_nodes)
+        records.append({
+            "roller_x_locations": [node_positions[t - 1] for t in rollers_b],
+            "force_x_locations": [node_positions[t - 1] for t in force_nodes],
+            "force_values": list(force_values),
+            "I_values": out["I"][b].tolist(),
+            "shear_forces": out["shear"][b, c].tolist(),
+            "bending_moments": out["moment"][b, c].tolist(),
+            "node_positions": node_positions.tolist(),
+            "roller_nodes": list(rollers_b),
+            "force_nodes": list(force_nodes),
+            "num_nodes": params.num_nodes,
+            "L": L_b,
+            "rotations": out["rot"][b, c].tolist(),
+            "deflections": out["defl"][b, c].tolist(),
+        })
+    return records
+
+
+def generate_samples_batched(sample_indices: Sequence[int], num_nodes: int, flag: int, L: float,
+                             node_positions, roller_nodes: Sequence[int], available_nodes: Sequence[int],
+                             patience: int = 10, device="cuda", *, params: Optional[BeamOptParams] = None,
+                             config: Optional[GeneratorConfig] = None, seed: Optional[int] = None,
+                             rng=None) -> List[Optional[dict]]:
+    """Batched ``generate_sample``: draws ``len(sample_indices)`` samples from ONE stream in index
+    order (exactly what the reference's serial loop SingleCore:256-257 would draw after
+    ``random.seed(seed)``), optimises them in one launch, returns the records in that order."""
+    cfg = config or GeneratorConfig()
+    p = (params or cfg.params).replace(num_nodes=num_nodes, patience=patience)
+    if rng is None:
+        rng = random if seed is None else random.Random(seed)
+    elif seed is not None:
+        raise ValueError("pass either seed or rng")
+    if seed is not None and rng is random:
+        random.seed(seed)
+    cases = [sampling.sample_case(num_nodes, flag, L, roller_nodes, available_nodes, L_max=cfg.L_max,
+                                  L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max,
+                                  M_forces_max=cfg.M_forces_max, max_force=cfg.max_force,
+                                  min_force=cfg.min_force, rng=rng)
+             for _ in range(len(sample_indices) * p.num_cases)]
+    out = optimise_cases(p, cases, device)
+    return make_records(p, cases, out)
+
+
+def generate_sample(sample_idx: int, num_nodes: int, flag: int, L: float, node_positions,
+                    roller_nodes: Sequence[int], available_nodes: Sequence[int], patience: int = 10,
+                    device="cuda", **kw) -> Optional[dict]:
+    """Drop-in for the reference's per-sample function (one beam per launch; use the batched form
+    for throughput).  Draws from the global ``random`` module like the reference."""
+    return generate_samples_batched([sample_idx], num_nodes, flag, L, node_positions, roller_nodes,
+                                    available_nodes, patience, device, **kw)[0]
+
+
+def generate_dataset(config: Optional[GeneratorConfig] = None, num_samples: Optional[int] = None,
+                     seed: Optional[int] = 0, device="cuda", batch_size: int = 65536) -> dict:
+    """``main()`` of the generators (SingleCore:251-269): dict-of-lists over all samples, failed
+    samples dropped (MultiCore:265).  Samples are drawn from one seeded stream in global order."""
+    cfg = config or GeneratorConfig()
+    p = cfg.params
+    N = cfg.num_samples if num_samples is None else num_samples
+    rollers, available = sampling.fixed_bridge(p.num_nodes, cfg.roller_nodes)
+    node_positions = np.linspace(0, cfg.L_max, p.num_nodes)
+    rng = random.Random(seed) if seed is not None else random
+    training_data = {k: [] for k in TRAINING_DATA_KEYS}
+    for start in range(0, N, batch_size):
+        idx = range(start, min(start + batch_size, N))
+        for rec in generate_samples_batched(idx, p.num_nodes, cfg.random_bridge, cfg.L_max, node_positions,
+                                            rollers, available, p.patience, device, params=p, config=cfg,
+                                            rng=rng):
+            if rec is None:
+                continue
+            for k in TRAINING_DATA_KEYS:
+                training_data[k].append(rec[k])
+    return training_data
+
+
+def save_training_data(training_data: dict, path: str = "training_data_PINN_mini.json") -> None:
+    """json.dump of the dict-of-lists, the file the trainers json.load (SingleCore:263-264, PINN:192-206)."""
+    def default(o):
+        if isinstance(o, (np.floating, np.integer)):
+            return o.item()
+        raise TypeError(type(o))
+    with open(path, "w") as f:
+        json.dump(training_data, f, default=default)

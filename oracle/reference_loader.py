@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE ONLY -- runs the reference's OWN generator source on top of the shim.
+
+Works only where ``/root/reference`` is mounted (the build container).  Nothing here is
+reachable from ``-m gpu`` tests, ``smoke()`` or ``bench.py``: those use the committed
+fixtures in ``tests/golden/`` that ``tests/golden/make_golden.py`` produces with this module.
+
+The reference scripts are flat modules whose tail (``if __name__ == '__main__': main()``
+followed by a module-level re-load of the JSON they just wrote, SingleCore:271-298) cannot
+be imported.  We therefore compile the script text only up to the ``__main__`` guard and
+execute it in a fresh namespace with ``openseespy.opensees`` resolved to
+``oracle.opensees_shim`` -- ``setup_model`` / ``generate_sample`` then run verbatim.
+No reference source is copied into the repository.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import types
+
+from . import opensees_shim
+
+REFERENCE_DIR = os.environ.get("OPENPYSTRUCT_REFERENCE_DIR", "/root/reference")
+
+SCRIPTS = {
+    "SC": "OpenPyStruct_BeamOpt_training_SingleCore.py",
+    "MC": "OpenPyStruct_BeamOpt_training_MultiCore.py",
+    "GPU": "OpenPyStruct_BeamOpt_training_GPU.py",
+}
+
+
+def reference_available() -> bool:
+    return all(os.path.isfile(os.path.join(REFERENCE_DIR, f)) for f in SCRIPTS.values())
+
+
+def _install_shim():
+    pkg = types.ModuleType("openseespy")
+    pkg.opensees = opensees_shim
+    pkg.__path__ = []
+    sys.modules["openseespy"] = pkg
+    sys.modules["openseespy.opensees"] = opensees_shim
+
+
+def load_generator(which: str) -> dict:
+    """Namespace of reference script ``which`` ('SC' | 'MC' | 'GPU') with main() not run."""
+    _install_shim()
+    path = os.path.join(REFERENCE_DIR, SCRIPTS[which])
+    with open(path, "r") as fh:
+        text = fh.read()
+    cut = text.index('if __name__ == "__main__":')
+    ns = {"__name__": f"_reference_{which}", "__file__": path}
+    exec(compile(text[:cut], path, "exec"), ns)
+    return ns
+
+
+class Trace:
+    """Per-epoch record taken at the shim boundary (what OpenSees would have seen/returned)."""
+
+    def __init__(self):
+        self.I = []       # element inertias handed to ops.element (fp32 values widened), per epoch
+        self.M = []       # eleResponse[2] per element (f64), per epoch
+        self.V = []       # eleResponse[1] per element (f64), per epoch
+
+
+def run_reference_sample(which: str, seed: int, *, flag: int = 0, patience=None, overrides=None,
+                         trace: bool = True):
+    """random.seed(seed); reference generate_sample(...) with that script's own main() arguments.
+
+    Returns (result_dict, Trace, params) where params are the module-level constants in effect.
+    """
+    ns = load_generator(which)
+    if overrides:
+        ns.update(overrides)
+    ns["flag"] = flag
+    tr = Trace()
+    real_analyze = opensees_shim.analyze
+
+    def analyze(n=1):
+        rc = real_analyze(n)
+        if trace and rc == 0:
+            d = opensees_shim._D
+            tags = sorted(d.elements)
+            tr.I.append([d.elements[t][4] for t in tags])
+            tr.M.append([float(d.ele_forces[t][2]) for t in tags])
+            tr.V.append([float(d.ele_forces[t][1]) for t in tags])
+        return rc
+
+    opensees_shim.analyze = analyze
+    try:
+        random.seed(seed)
+        args = (0, ns["num_nodes"], flag, ns["L"], ns["node_positions"],
+                list(ns["roller_nodes"]), list(ns["available_nodes"]))
+        if which == "MC":
+            # MultiCore:259-261 -- patience is NOT forwarded, the def default (10) applies.
+            kwargs = {} if patience is None else {"patience": patience}
+        elif which == "SC":
+            kwargs = {"patience": ns["patience"] if patience is None else patience}   # SingleCore:257
+        else:
+            kwargs = {"patience": ns["patience"] if patience is None else patience, "device": "cpu"}
+        result = ns["generate_sample"](*args, **kwargs)
+    finally:
+        opensees_shim.analyze = real_analyze
+    params = {k: ns[k] for k in ("E", "nu", "G", "A", "L_max", "num_nodes", "max_force", "min_force",
+                                 "uniform_udl", "I_0", "max_e", "lr", "gamma", "alpha_moment",
+                                 "alpha_shear", "tolerance", "patience", "L_min", "N_rollers_max",
+                                 "M_forces_max")}
+    return result, tr, params

@@ -1,0 +1,100 @@
+"""The kernel's per-beam arithmetic (openpystruct_b200/csrc/beamopt_core.cuh) compiled for the host
+(tests/hostsim -- debug aid, not a product path) against the CPU oracle.  This is how the exact
+operation order the GPU executes is validated in the build container, which has no GPU; the same
+comparisons run against the real kernel in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from openpystruct_b200 import sampling
+from openpystruct_b200.params import BeamOptParams
+from tests.helpers import (goldens, golden_params, golden_case, hostsim_run, hostsim_solve, oracle_params,
+                           oracle_run, rel_err, seeded_cases)
+
+
+@pytest.mark.parametrize("script,flag,count", [("SC", 0, 200), ("MC", 0, 200), ("GPU", 0, 40), ("SC", 1, 200)])
+def test_full_loop_against_c_oracle(script, flag, count):
+    p = BeamOptParams.for_script(script)
+    cases = seeded_cases(p, count, seed=11, flag=flag)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    a = oracle_run(p, fixed, fn, fv, L)
+    b = hostsim_run(p, fixed, fn, fv, L)
+    assert not a["status"].any() and not b["status"].any()
+    same = a["epochs"] == b["epochs"]
+    # identical early-stop decisions (both sides IEEE fp32; M,V agree to ~1e-11 before the fp32 cast)
+    assert same.mean() >= (0.99 if flag == 0 else 0.97)
+    tol = 1e-5
+    assert np.max(np.abs(a["I"][same] - b["I"][same]) / a["I"][same]) < tol
+    assert (a["I"][same] == b["I"][same]).mean() > 0.98
+    assert rel_err(b["defl"][same, 0], a["defl"][same, 0]).max() < (1e-7 if flag == 0 else 1e-5)
+    assert np.array_equal(a["loss"][same] == b["loss"][same], np.ones(same.sum(), bool)) or \
+        (a["loss"][same] == b["loss"][same]).mean() > 0.98
+
+
+def test_fixed_epoch_mode_against_c_oracle():
+    p = BeamOptParams.for_script("MC").replace(early_stop=False, max_e=600)
+    cases = seeded_cases(p, 50, seed=12)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    a = oracle_run(p, fixed, fn, fv, L)
+    b = hostsim_run(p, fixed, fn, fv, L)
+    assert (a["epochs"] == 600).all() and (b["epochs"] == 600).all()
+    assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
+    assert (a["defl"][:, 0, -1] == 0).all() and (b["defl"][:, 0, -1] == 0).all()     # MultiCore:222-223
+
+
+def test_single_solve_1e9_on_default_bridge_and_vs_truth():
+    p = BeamOptParams()
+    rng = np.random.default_rng(0)
+    cases = seeded_cases(p, 200, seed=13)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    I = np.exp(rng.uniform(np.log(3e-3), np.log(0.9), (200, 100))).astype(np.float32).astype(np.float64)
+    cp = oracle_params(p)
+    o64 = c_oracle.beam_solve(cp, fixed, fn[:, 0], fv[:, 0], L, I, 0)
+    o80 = c_oracle.beam_solve(cp, fixed, fn[:, 0], fv[:, 0], L, I, 1)
+    h = hostsim_solve(p, fixed, fn[:, 0], fv[:, 0], L, I)
+    for k in ("defl", "rot", "shear", "moment"):
+        assert rel_err(h[k], o64[k]).max() < 1e-9, k      # north_star tolerance vs the dpbsv restatement
+        assert rel_err(h[k], o80[k]).max() < 5e-10, k     # and vs the extended-precision truth
+
+
+def test_single_solve_on_reference_goldens():
+    for m, rec in goldens():
+        p = golden_params(m)
+        fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, [golden_case(m)])
+        h = hostsim_solve(p, fixed, fn[:, 0], fv[:, 0], L, rec["I_last"][None, :])
+        tol = 1e-9 if m["flag"] == 0 else 1e-6
+        assert rel_err(h["moment"][0], rec["M64_last"]) < tol
+        assert rel_err(h["shear"][0], rec["V64_last"]) < tol
+
+
+def test_goldens_full_loop():
+    same = 0
+    for m, rec in goldens():
+        p = golden_params(m)
+        fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, [golden_case(m)])
+        b = hostsim_run(p, fixed, fn, fv, L)
+        if b["epochs"][0] == m["epochs"]:
+            same += 1
+            assert np.max(np.abs(b["I"][0] - rec["I_values"]) / rec["I_values"]) < 1e-5
+            assert rel_err(b["moment"][0, 0], rec["bending_moments"]) < 1e-6
+    assert same >= 0.8 * len(goldens())
+
+
+def test_edge_cases():
+    p = BeamOptParams.for_script("SC").replace(max_e=40)
+    cases = [
+        (200.0, [10, 30, 70, 85, 100], [], []),                       # UDL only
+        (200.0, [101], [51], [-1e5]),                                 # single span, roller at the tip node
+        (15.0, [2], [3, 4, 5, 6], [-3.5e5] * 4),                      # shortest random bridge, roller next to the pin
+        (215.0, [100], [2, 50, 99, 60], [-3e5, -2e5, -1e5, -5e4]),   # longest, one roller
+        (200.0, [10, 30, 70, 85, 100], [50, 50], [-1e5, -1e5]),       # two loads on one node accumulate
+    ]
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    a = oracle_run(p, fixed, fn, fv, L)
+    b = hostsim_run(p, fixed, fn, fv, L)
+    assert np.array_equal(a["epochs"], b["epochs"]) and not b["status"].any()
+    assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
+    # mechanism: pin only (no roller) is singular -> status 1 on both sides, never a crash
+    fixed2, fn2, fv2, L2 = sampling.pack_cases(p.num_nodes, p.max_forces, [(200.0, [], [50], [-1e5])])
+    assert oracle_run(p, fixed2, fn2, fv2, L2)["status"][0] == 1
+    assert hostsim_run(p, fixed2, fn2, fv2, L2)["status"][0] == 1
