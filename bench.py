@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: optimised beams/s at a fixed epoch count (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA kernel behind the C ABI)
+  python bench.py --impl reference [...]                       reference arm: the reference's CPU path
+                                                               (torch-path port, all host cores)
+  torchrun --nproc-per-node N bench.py --gpus N ...            one rank per GPU
+
+A "step" is one pass of the fused optimisation loop over one batch of synthetic beams: BASELINE
+configs[1] -- 10 000 beams per GPU, default discretisation (101 nodes, rollers 10/30/70/85/100, UDL
+-1000, 1-4 point loads), max_e = 600 epochs with early stopping disabled (E_fix).
+Inputs come from the seeded host sampler (the reference's draw order) and are resident in HBM before
+the timed region; L2 is flushed between steps.  For N > 1 every rank optimises its own 10 000 beams
+(weak scaling) and the per-step dataset all_gather over NCCL is inside the timed step.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "optimised beams/s (fixed 600 epochs)"
+UNIT = "beams/s"
+BEAMS_PER_GPU = 10000
+EPOCHS = 600
+NUM_NODES = 101
+# algorithmic FP64 work per beam-iteration: assembly 8n + band LDL^T 16N + solves 13N +
+# force recovery 16n = 82n + 58 with n elements, N = 2(n+1) DOFs (FMA = 2, div = sqrt = 1)
+F64_FLOP_PER_ITER = 82 * (NUM_NODES - 1) + 58
+# algorithmic HBM bytes per beam: inputs (fixed_uy nn + force nodes/values 4*(4+8) + L 8) and
+# outputs (I 4n, shear 4n, moment 4n, defl 8nn, rot 8nn, epochs/loss/status 12)
+BYTES_PER_BEAM = (NUM_NODES + 4 * 12 + 8) + (12 * (NUM_NODES - 1) + 16 * NUM_NODES + 12)
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 DFMA lanes/SM x 148 SMs x max SM clock
+
+
+def workload_params(early_stop=False):
+    from openpystruct_b200.params import BeamOptParams
+    return BeamOptParams.for_script("MC").replace(early_stop=early_stop, max_e=EPOCHS)
+
+
+def sample_inputs(beams, seed):
+    import random
+    from openpystruct_b200 import sampling
+    p = workload_params()
+    rng = random.Random(seed)
+    rollers, avail = sampling.fixed_bridge(p.num_nodes)
+    cases = [sampling.sample_case(p.num_nodes, 0, 200.0, rollers, avail, rng=rng) for _ in range(beams)]
+    return sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [x.strip() for x in row.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baselines (the oracle is only ever the thing measured HERE, never on the product path)
+# --------------------------------------------------------------------------------------------------
+def cpu_torch_port(beams, workers):
+    """The reference's torch path (port) over a process pool, MultiCore:258 pattern, E_fix = 600."""
+    from oracle import beamopt_port as port
+    p = port.BeamOptParams.for_script("MC")
+    p.early_stop = False
+    p.max_e = EPOCHS
+    done, dt = port.timed_pool_run(p, beams, workers, seed=1234)
+    return done / dt, done, dt
+
+
+def cpu_c_oracle(beams, workers):
+    """The plain-C restatement on `workers` threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tests.helpers import oracle_run
+    p = workload_params()
+    fixed, fn, fv, L = sample_inputs(beams, seed=4321)
+    chunks = np.array_split(np.arange(beams), workers)
+    oracle_run(p, fixed[:1], fn[:1], fv[:1], L[:1])        # build + warm
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(workers) as ex:
+        list(ex.map(lambda c: oracle_run(p, fixed[c], fn[c], fv[c], L[c]) if len(c) else None, chunks))
+    dt = time.perf_counter() - t0
+    return beams / dt, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import beamopt_port as port
+    cores = host_cores()
+    beams_per_step = max(cores * 2, 8)
+    p = port.BeamOptParams.for_script("MC")
+    p.early_stop = False
+    p.max_e = EPOCHS
+    pool = port.PortPool(p, cores)
+    try:
+        for _ in range(args.warmup):
+            pool.run(max(cores, 4))
+        times = []
+        for _ in range(max(args.steps, 1)):
+            done, dt = pool.run(beams_per_step)
+            assert done == beams_per_step
+            times.append(dt)
+    finally:
+        pool.close()
+    value = beams_per_step * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: BeamOpt_training_MultiCore dataset, default discretisation, "
+                               "600 fixed epochs; bounded sample per step", "beams_per_step": beams_per_step,
+                   "num_nodes": NUM_NODES, "epochs": EPOCHS, "early_stop": False},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{beams_per_step} beams x {EPOCHS} epochs per step on a {cores}-process pool: "
+                                   "reference torch path (torch.sum/autograd/Adam/ExponentialLR on CPU) with the "
+                                   "OpenSees half restated (scipy dpbsv); OpenSeesPy is not installable offline"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openpystruct_b200 import _cabi, ops
+    from openpystruct_b200.distributed import gather_outputs, init_from_env
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    rank, local, world = init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    p = workload_params()
+    B = BEAMS_PER_GPU
+    fixed, fn, fv, L = sample_inputs(B, seed=1000 + rank)
+    h_in = [torch.from_numpy(a).pin_memory() for a in (fixed, fn, fv, L)]
+    d_in = [t.to(dev) for t in h_in]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        out = ops.optimise_beams(p, *d_in)
+        if world > 1:
+            out = gather_outputs(out, B * world)
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    assert int(out["epochs"].min()) == EPOCHS and int(out["status"].sum()) == 0
+
+    # kernel-only duration (no gather), for the roofline of the dominant kernel
+    kev = []
+    for _ in range(min(args.steps, 5)):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.optimise_beams(p, *d_in); e1.record()
+        kev.append((e0, e1))
+    torch.cuda.synchronize()
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+
+    # end to end through the C ABI with HOST buffers (H2D + D2H inside): ops_beamopt_run_host
+    e2e_steps = min(args.steps, 5)
+    _cabi.run_host(p, fixed, fn, fv, L, device=local)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_out = _cabi.run_host(p, fixed, fn, fv, L, device=local)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(e2e_s.item())
+    h2d = sum(a.nbytes for a in (fixed, fn, fv, L)) + 8 * p.max_e
+    d2h = sum(v.nbytes for k, v in host_out.items() if k != "kernel_ms")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * B * args.steps / (total_ms * 1e-3)
+    # FP64 roofline of the dominant kernel (algorithmic flops only; DDIV expansion etc. not credited)
+    tf_measured, _ = _cabi.fp64_peak_probe(1 << 16, torch.cuda.current_stream().cuda_stream)
+    achieved_tf = B * EPOCHS * F64_FLOP_PER_ITER / (kernel_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_achieved = B * BYTES_PER_BEAM / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    cores = host_cores()
+    cpu = None
+    cpu_c = None
+    if not args.no_cpu_baseline and world == 1:
+        sample_beams = max(cores * 4, 16)
+        rate, done, dt = cpu_torch_port(sample_beams, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{done} beams x {EPOCHS} fixed epochs in {dt:.1f} s on a {cores}-process pool "
+                         "(reference torch path port: real torch.sum/autograd/Adam on CPU + scipy dpbsv for "
+                         "the OpenSees half; OpenSeesPy not installable offline)"}
+        c_beams = max(cores * 150, 600)
+        c_rate, c_dt = cpu_c_oracle(c_beams, cores)
+        cpu_c = {"value": c_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                 "sample": f"{c_beams} beams x {EPOCHS} fixed epochs in {c_dt:.1f} s, plain-C restatement "
+                           f"(oracle/csrc) on {cores} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: BeamOpt_training_MultiCore dataset, 10k beams per GPU, "
+                               "default discretisation, 600 fixed epochs (early stop off)",
+                   "beams_per_gpu": B, "num_nodes": NUM_NODES, "epochs": EPOCHS, "early_stop": False,
+                   "fe_precision": "f64", "optimiser_precision": "f32 (torch CPU op order)",
+                   "l2": "flushed between steps (256 MiB write)", "collective": "all_gather of the dataset per "
+                   "step" if world > 1 else "none"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "path": "ops_beamopt_run_host (C ABI, host buffers, H2D+D2H+alloc inside)"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": tf_measured, "unit": "TFLOP/s",
+                     "frac": achieved_tf / tf_measured, "traffic": traffic,
+                     "peak_source": "measured in this run by ops_fp64_peak_probe (pure DFMA kernel); "
+                                    f"nominal {NOMINAL_FP64_TFLOPS:.1f} TFLOP/s = 148 SM x 64 DFMA/clk x 1.965 GHz; "
+                                    "MEASURED_PEAKS.json has no FP64 entry",
+                     "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
+                     "kernel": "beamopt_kernel", "kernel_ms": kernel_ms,
+                     "flop_per_beam_iteration": F64_FLOP_PER_ITER,
+                     "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": hbm_achieved / hbm_peak, "bytes_per_beam": BYTES_PER_BEAM,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}},
+        "cpu_baseline": cpu,
+        "cpu_baseline_c": cpu_c,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

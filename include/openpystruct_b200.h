@@ -136,6 +136,14 @@ int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
                          float *moment, int32_t *epochs, float *loss, int32_t *status,
                          int device, float *elapsed_ms);
 
+/*
+ * Diagnostic for the roofline denominator (no reference counterpart): runs `chains` independent
+ * DFMA chains of length `iters` per thread on a full grid of the current device and reports the
+ * sustained FP64 rate in TFLOP/s (FMA = 2 flop), timed with CUDA events on `cuda_stream`.
+ * Synchronises the stream.
+ */
+int ops_fp64_peak_probe(int iters, double *tflops, float *elapsed_ms, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ _lib = None
 EXPORTS = (
     "ops_beamopt_version", "ops_device_count", "ops_set_device", "ops_beamopt_fill_schedule",
     "ops_beamopt_workspace_bytes", "ops_beamopt_launch", "ops_beamsolve_launch", "ops_beamopt_run_host",
+    "ops_fp64_peak_probe",
 )
 
 
@@ -64,6 +65,7 @@ def lib():
             [C.c_void_p]
         L.ops_beamopt_run_host.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 12 + \
             [C.c_int, C.POINTER(C.c_float)]
+        L.ops_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p]
         _lib = L
     return _lib
 
@@ -112,3 +114,10 @@ def run_host(p: BeamOptParams, fixed_uy, force_nodes, force_vals, L, device: int
     check(rc, "ops_beamopt_run_host")
     out["kernel_ms"] = float(ms.value)
     return out
+
+
+def fp64_peak_probe(iters: int = 1 << 16, stream: int = 0):
+    """(TFLOP/s, ms) of a pure DFMA kernel on the current device -- the FP64 roofline denominator."""
+    tf, ms = C.c_double(0.0), C.c_float(0.0)
+    check(lib().ops_fp64_peak_probe(iters, C.byref(tf), C.byref(ms), stream), "ops_fp64_peak_probe")
+    return float(tf.value), float(ms.value)

@@ -284,6 +284,20 @@ static int plan_launch(const BeamConsts &k, int64_t B, LaunchPlan *pl)
     return 0;
 }
 
+// DFMA throughput probe: 8 independent chains per thread keep the FP64 pipe full.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double seed, double *sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) sink[0] = s;     // never true; keeps the chains alive
+}
+
 }  // namespace ops
 
 using namespace ops;
@@ -430,6 +444,36 @@ int ops_beamsolve_launch(const OpsBeamOptParams *p, int64_t B,
     }
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
+}
+
+int ops_fp64_peak_probe(int iters, double *tflops, float *elapsed_ms, void *cuda_stream)
+{
+    if (iters <= 0 || !tflops) return OPS_E_BADARG;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    double *sink = nullptr;
+    cudaEvent_t ev0, ev1;
+    e = cudaMalloc((void **)&sink, 8);
+    if (e != cudaSuccess) return (int)e;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    const int blocks = sms * 8, threads = 256;
+    fp64_probe_kernel<<<blocks, threads, 0, stream>>>(iters / 8 + 1, 1.0, sink);   // warm-up
+    cudaEventRecord(ev0, stream);
+    fp64_probe_kernel<<<blocks, threads, 0, stream>>>(iters, 1.0, sink);
+    cudaEventRecord(ev1, stream);
+    e = cudaStreamSynchronize(stream);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaFree(sink);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / ((double)ms * 1e-3) / 1e12;
+    if (elapsed_ms) *elapsed_ms = ms;
+    return 0;
 }
 
 #define OPS_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (int)e_; goto done; } } while (0)

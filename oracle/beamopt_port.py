@@ -309,16 +309,36 @@ def _worker(args):
     return done
 
 
-def timed_pool_run(p: BeamOptParams, beams: int, workers: int, seed: int = 0, flag: int = 0):
-    """MultiCore:258 pattern (process pool over beams).  Returns (beams_done, seconds)."""
-    import multiprocessing as mp
-    import time
-    per = [beams // workers + (1 if i < beams % workers else 0) for i in range(workers)]
-    jobs = [(p, seed + 7919 * i, c, flag) for i, c in enumerate(per) if c > 0]
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(len(jobs)) as pool:
-        pool.map(_worker, [(p, 0, 0, flag)] * len(jobs))   # warm: import torch in every worker
+class PortPool:
+    """Process pool over beams (the MultiCore:258 joblib/loky pattern) kept alive across timed steps."""
+
+    def __init__(self, p: BeamOptParams, workers: int, flag: int = 0):
+        import multiprocessing as mp
+        self.p, self.workers, self.flag = p, workers, flag
+        self.pool = mp.get_context("spawn").Pool(workers)
+        self.pool.map(_worker, [(p, 0, 0, flag)] * workers)          # import torch in every worker
+        self.calls = 0
+
+    def run(self, beams: int, seed: int = 0):
+        """Optimise `beams` freshly sampled beams; returns (beams_done, seconds)."""
+        import time
+        w = self.workers
+        per = [beams // w + (1 if i < beams % w else 0) for i in range(w)]
+        self.calls += 1
+        jobs = [(self.p, seed + 7919 * i + 104729 * self.calls, c, self.flag) for i, c in enumerate(per) if c > 0]
         t0 = time.perf_counter()
-        done = sum(pool.map(_worker, jobs, chunksize=1))
-        dt = time.perf_counter() - t0
-    return done, dt
+        done = sum(self.pool.map(_worker, jobs, chunksize=1))
+        return done, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def timed_pool_run(p: BeamOptParams, beams: int, workers: int, seed: int = 0, flag: int = 0):
+    """One-shot PortPool run.  Returns (beams_done, seconds)."""
+    pool = PortPool(p, workers, flag)
+    try:
+        return pool.run(beams, seed)
+    finally:
+        pool.close()
