@@ -36,6 +36,15 @@ extern "C" {
 #define OPS_E_UNSUPP   (-2)   /* configuration outside what the kernels implement */
 #define OPS_E_WORKSPACE (-3)  /* workspace too small */
 
+/* per-beam status[] values */
+#define OPS_STATUS_OK          0
+#define OPS_STATUS_SINGULAR    1   /* mechanism / non-SPD pivot / non-finite result: drop the sample */
+#define OPS_STATUS_UNSUPPORTED 3   /* OPS_SOLVER_THREE_MOMENT only: more than 5 rollers; use OPS_SOLVER_BAND_LDLT */
+
+/* solver selection */
+#define OPS_SOLVER_THREE_MOMENT 0  /* exact Schur complement of K onto the support moments (default, fastest) */
+#define OPS_SOLVER_BAND_LDLT    1  /* in-place banded (block) LDL^T of K, factor kept in shared memory */
+
 /* Module-level constants of the reference generators (SingleCore:20-49, MultiCore:20-52, GPU:21-56,
  * BeamOpt:24-48) plus the literals of the loss (SingleCore:195-196) and torch's Adam defaults. */
 typedef struct OpsBeamOptParams {
@@ -47,6 +56,8 @@ typedef struct OpsBeamOptParams {
     int32_t patience;        /* SC 5, MC 10 (def default shadows the constant), GPU 100, BeamOpt 10 */
     int32_t early_stop;      /* 1 = reference behaviour; 0 = run exactly max_epochs (benchmark mode) */
     int32_t zero_last_node;  /* 1 = MultiCore:222-223 emits 0.0 for the last node's uy / theta */
+    int32_t solver;          /* OPS_SOLVER_*: how K(I) u = f is solved each epoch (results agree to ~1e-10) */
+    int32_t reserved;        /* must be 0 */
     double E;                /* 200e9 */
     double G;                /* E / (2 (1 + nu)) */
     double udl;              /* uniform_udl (-1000; BeamOpt -5000), applied to every element */

@@ -23,7 +23,8 @@ class OpsBeamOptParams(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("num_nodes", C.c_int32), ("num_cases", C.c_int32),
         ("max_forces", C.c_int32), ("max_epochs", C.c_int32), ("patience", C.c_int32),
-        ("early_stop", C.c_int32), ("zero_last_node", C.c_int32),
+        ("early_stop", C.c_int32), ("zero_last_node", C.c_int32), ("solver", C.c_int32),
+        ("reserved", C.c_int32),
         ("E", C.c_double), ("G", C.c_double), ("udl", C.c_double), ("I0", C.c_double),
         ("lr", C.c_double), ("gamma", C.c_double), ("alpha_moment", C.c_double),
         ("alpha_shear", C.c_double), ("tolerance", C.c_double), ("shear_k", C.c_double),
@@ -39,7 +40,7 @@ class CudaLibraryError(RuntimeError):
 def to_c_params(p: BeamOptParams) -> OpsBeamOptParams:
     return OpsBeamOptParams(
         C.sizeof(OpsBeamOptParams), p.num_nodes, p.num_cases, p.max_forces, p.max_e, p.patience,
-        int(p.early_stop), int(p.zero_last_node), p.E, p.G, p.uniform_udl, p.I_0, p.lr, p.gamma,
+        int(p.early_stop), int(p.zero_last_node), int(p.solver), 0, p.E, p.G, p.uniform_udl, p.I_0, p.lr, p.gamma,
         p.alpha_moment, p.alpha_shear, p.tolerance, p.shear_k, p.bending_eps, p.clamp_min,
         p.beta1, p.beta2, p.adam_eps)
 

@@ -17,6 +17,7 @@
 
 #include "../../include/openpystruct_b200.h"
 #include "beamopt_core.cuh"
+#include "beamopt_flex.cuh"
 
 #define OPS_VERSION "openpystruct_b200 0.1.0 sm_100a"
 
@@ -152,6 +153,125 @@ __global__ void __launch_bounds__(128) beamopt_kernel(const BeamConsts k, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Production kernel: three-moment iteration (beamopt_flex.cuh), one thread per beam, persistent
+// lanes.  Per-beam state: fp32 I (double-buffered: the analysed and the updated vector), Adam m, v,
+// the running torch.sum partials and the O(#supports) span store.  `lay` says which of the fp32
+// arrays live in shared memory and which in an L2-resident global scratch laid out [e][thread].
+// ---------------------------------------------------------------------------------------------
+struct FlexLayout {
+    int I_global, m_global, v_global;   // 0 = shared memory, 1 = global scratch
+    int nacc;                           // running-sum slots per reduction (32, or 64 with the level cascade)
+};
+
+__global__ void __launch_bounds__(256) beamopt_flex_kernel(const BeamConsts k, const long long B, const OptPtrs p,
+                                                           const FlexLayout lay)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    const int n = k.n, nn = k.nn;
+    const long total = (long)gridDim.x * T;
+    const long gtid = (long)blockIdx.x * T + threadIdx.x;
+
+    // carve shared memory: doubles, then floats, then ints
+    double *sd = reinterpret_cast<double *>(smem_raw);
+    float *sf = reinterpret_cast<float *>(sd + (size_t)FlexStore::NUM_DOUBLES * T);
+    FlexStore fs;
+    fs.sd = sd + threadIdx.x;
+    fs.stride = T;
+    OptState os;
+    float *gf = p.ws_f + gtid;          // global scratch arrays: which * n * total
+    int gslot = 0;
+    auto place = [&](int global, int count, float *&ptr, long &stride) {
+        if (global) { ptr = gf + (long)gslot * n * total; stride = total; gslot += 1; (void)count; }
+        else { ptr = sf + threadIdx.x; stride = T; sf += (size_t)count * T; }
+    };
+    place(lay.I_global, n, os.Icur, os.sI);
+    place(lay.I_global, n, os.Inext, os.sIn);
+    place(lay.m_global, n, os.m, os.sm);
+    place(lay.v_global, n, os.v, os.sv);
+    os.accd = sf + threadIdx.x; sf += (size_t)lay.nacc * T;
+    os.accq = sf + threadIdx.x; sf += (size_t)lay.nacc * T;
+    os.sacc = T;
+    fs.si = reinterpret_cast<int *>(sf) + threadIdx.x;
+
+    FlexBeam fb;
+    long long b = -1;
+    bool have = false, exhausted = false;
+    int t = 0, counter = 0, bad = 0;
+    double best = INFINITY;
+    float lossf = NAN;
+
+    while (true) {
+        if (!have && !exhausted) {
+            b = (long long)atomicAdd(p.counter, 1ULL);
+            if (b < B) {
+                have = true;
+                t = 0; counter = 0; best = INFINITY; lossf = NAN;
+                int fnode[FLEX_MAXF];
+                double fval[FLEX_MAXF];
+                for (int j = 0; j < k.max_forces; ++j) {
+                    fnode[j] = p.force_nodes[b * k.max_forces + j];
+                    fval[j] = p.force_vals[b * k.max_forces + j];
+                }
+                const uint8_t *fx = p.fixed_uy + b * nn;
+                bad = flex_setup(k, p.L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode, fval, fs, fb);
+                for (int e = 0; e < n; ++e) {
+                    os.Icur[(long)e * os.sI] = k.I0f;
+                    os.Inext[(long)e * os.sIn] = k.I0f;
+                    os.m[(long)e * os.sm] = 0.0f;
+                    os.v[(long)e * os.sv] = 0.0f;
+                }
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            bool done = (k.max_epochs <= 0) || (bad != 0);
+            if (!done) {
+                int rc = 0;
+                const float neg_step = __ldg(p.sched + 2 * t);
+                const float bc2_sqrt = __ldg(p.sched + 2 * t + 1);
+                lossf = flex_iteration(k, fb, fs, os, neg_step, bc2_sqrt, &rc);
+                ++t;
+                // ping-pong: Icur <- updated inertias, Inext <- the vector that was just analysed
+                { float *tp = os.Icur; os.Icur = os.Inext; os.Inext = tp; long ts = os.sI; os.sI = os.sIn; os.sIn = ts; }
+                if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
+                if (k.early_stop) {
+                    const double l = (double)lossf;
+                    if (l < best - k.tol) { best = l; counter = 0; } else { ++counter; }
+                    if (counter >= k.patience) done = true;
+                }
+                if (t >= k.max_epochs) done = true;
+            }
+            if (done) {
+                const bool fields = (t > 0) && (bad == 0);
+                for (int e = 0; e < n; ++e) p.I_values[b * n + e] = os.Icur[(long)e * os.sI];
+                if (fields) {
+                    flex_forces_march(k, fb, fs, [&](int e, double V, double M) {
+                        p.shear[b * n + e] = (float)V;
+                        p.moment[b * n + e] = (float)M;
+                    });
+                    flex_deflections_march(k, fb, fs, [&](int e) { return (double)os.Inext[(long)e * os.sIn]; },
+                                           [&](int i, double u, double th) {
+                                               const bool z = k.zero_last_node && i == nn - 1;
+                                               p.defl[b * nn + i] = z ? 0.0 : u;
+                                               p.rot[b * nn + i] = z ? 0.0 : th;
+                                           });
+                } else {
+                    for (int e = 0; e < n; ++e) { p.shear[b * n + e] = 0.0f; p.moment[b * n + e] = 0.0f; }
+                    for (int i = 0; i < nn; ++i) { p.defl[b * nn + i] = 0.0; p.rot[b * nn + i] = 0.0; }
+                }
+                p.epochs[b] = t;
+                p.loss[b] = lossf;
+                p.status[b] = bad;
+                have = false;
+            }
+        }
+    }
+}
+
 struct SolvePtrs {
     const uint8_t *fixed_uy;
     const int32_t *force_nodes;
@@ -199,12 +319,50 @@ __global__ void __launch_bounds__(128) beamsolve_kernel(const BeamConsts k, cons
     p.status[b] = rc;
 }
 
+// One three-moment solve per beam (FP64 outputs); span store in shared memory.
+__global__ void __launch_bounds__(128) beamsolve_flex_kernel(const BeamConsts k, const long long B, const SolvePtrs p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x;
+    const int n = k.n, nn = k.nn;
+    const long long b = (long long)blockIdx.x * T + threadIdx.x;
+    if (b >= B) return;
+    FlexStore fs;
+    fs.sd = reinterpret_cast<double *>(smem_raw) + threadIdx.x;
+    fs.si = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)FlexStore::NUM_DOUBLES * T) + threadIdx.x;
+    fs.stride = T;
+    FlexBeam fb;
+    int fnode[FLEX_MAXF];
+    double fval[FLEX_MAXF];
+    for (int j = 0; j < k.max_forces; ++j) {
+        fnode[j] = p.force_nodes[b * k.max_forces + j];
+        fval[j] = p.force_vals[b * k.max_forces + j];
+    }
+    const uint8_t *fx = p.fixed_uy + b * nn;
+    const double *Ib = p.I + b * n;
+    int bad = flex_setup(k, p.L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode, fval, fs, fb);
+    if (!bad) {
+        bad = flex_support_moments(k, fb, fs, [&](int e) { return Ib[e]; });
+        flex_forces_march(k, fb, fs, [&](int e, double V, double M) {
+            p.shear[b * n + e] = V;
+            p.moment[b * n + e] = M;
+        });
+        flex_deflections_march(k, fb, fs, [&](int e) { return Ib[e]; }, [&](int i, double u, double th) {
+            p.defl[b * nn + i] = u;
+            p.rot[b * nn + i] = th;
+        });
+    }
+    p.status[b] = bad;
+}
+
 static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
 {
     if (!p || p->struct_size != (int32_t)sizeof(OpsBeamOptParams)) return OPS_E_BADARG;
     if (p->num_nodes < 2 || p->num_cases < 1 || p->max_forces < 0 || p->max_epochs < 0) return OPS_E_BADARG;
     if (p->num_cases != 1) return OPS_E_UNSUPP;
     if (p->max_forces > 8) return OPS_E_UNSUPP;
+    if (p->solver != OPS_SOLVER_THREE_MOMENT && p->solver != OPS_SOLVER_BAND_LDLT) return OPS_E_BADARG;
+    if (p->reserved != 0) return OPS_E_BADARG;
     k->nn = p->num_nodes;
     k->n = p->num_nodes - 1;
     k->max_forces = p->max_forces;
@@ -231,6 +389,8 @@ static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
 }
 
 struct LaunchPlan {
+    bool flex;           // three-moment kernel
+    FlexLayout lay;
     bool smem;
     int threads;         // per CTA
     int blocks;
@@ -244,7 +404,50 @@ static size_t per_beam_bytes(int nn)
     return (size_t)5 * nn * 8 + (size_t)3 * n * 4 + (size_t)((nn + 31) / 32) * 4;
 }
 
-static int plan_launch(const BeamConsts &k, int64_t B, LaunchPlan *pl)
+static size_t flex_smem_per_thread(int n, const FlexLayout &lay)
+{
+    const int smem_arrays = (lay.I_global ? 0 : 2) + (lay.m_global ? 0 : 1) + (lay.v_global ? 0 : 1);
+    return (size_t)FlexStore::NUM_DOUBLES * 8 + ((size_t)smem_arrays * n + 2 * (size_t)lay.nacc) * 4 +
+           (size_t)FlexStore::NUM_INTS * 4;
+}
+
+static int plan_flex(const BeamConsts &k, int64_t B, int sms, int smem_optin, LaunchPlan *pl)
+{
+    memset(pl, 0, sizeof *pl);
+    pl->flex = true;
+    pl->lay.nacc = (k.n / 32) >= 16 ? 64 : 32;
+    // Layout: more resident warps beat keeping everything in shared memory (profiles/): by default
+    // Adam's m, v go to the L2-resident global scratch, I stays in shared memory; when even that
+    // leaves fewer than 64 threads per SM (fine discretisations) I moves out as well.
+    // OPS_FLEX_LAYOUT = smem | mv | all and OPS_FLEX_THREADS override (profiling knobs).
+    const char *lay_env = getenv("OPS_FLEX_LAYOUT");
+    const char *thr_env = getenv("OPS_FLEX_THREADS");
+    int mode = 1;
+    if (lay_env) mode = !strcmp(lay_env, "smem") ? 0 : (!strcmp(lay_env, "all") ? 2 : 1);
+    for (;; ++mode) {
+        pl->lay.I_global = mode >= 2;
+        pl->lay.m_global = pl->lay.v_global = mode >= 1;
+        const size_t per = flex_smem_per_thread(k.n, pl->lay);
+        int T = (int)((size_t)smem_optin / per) / 32 * 32;
+        if (T > 256) T = 256;
+        if (thr_env && atoi(thr_env) >= 32 && atoi(thr_env) <= T) T = atoi(thr_env) / 32 * 32;
+        if (T >= 64 || mode >= 2) {
+            if (T < 32) return OPS_E_UNSUPP;
+            pl->threads = T;
+            pl->smem_bytes = per * T;
+            break;
+        }
+    }
+    const long want = (long)((B + pl->threads - 1) / pl->threads);
+    pl->blocks = (int)(want < sms ? want : sms);
+    if (pl->blocks < 1) pl->blocks = 1;
+    const size_t total = (size_t)pl->blocks * pl->threads;
+    const int garrays = (pl->lay.I_global ? 2 : 0) + (pl->lay.m_global ? 1 : 0) + (pl->lay.v_global ? 1 : 0);
+    pl->ws_f_bytes = total * garrays * k.n * 4;
+    return 0;
+}
+
+static int plan_launch(const BeamConsts &k, int64_t B, int solver, LaunchPlan *pl)
 {
     int dev = 0, sms = 0, smem_optin = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -253,6 +456,7 @@ static int plan_launch(const BeamConsts &k, int64_t B, LaunchPlan *pl)
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return (int)e;
+    if (solver == OPS_SOLVER_THREE_MOMENT) return plan_flex(k, B, sms, smem_optin, pl);
     const size_t pb = per_beam_bytes(k.nn);
     memset(pl, 0, sizeof *pl);
     // experiment knobs (profiling only): OPS_BEAMOPT_GLOBAL=1 forces the global-scratch variant,
@@ -343,7 +547,7 @@ size_t ops_beamopt_workspace_bytes(const OpsBeamOptParams *p, int64_t B)
     BeamConsts k;
     if (make_consts(p, &k) != 0 || B < 0) return 0;
     LaunchPlan pl;
-    if (plan_launch(k, B, &pl) != 0) return 0;
+    if (plan_launch(k, B, p->solver, &pl) != 0) return 0;
     return 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
 }
 
@@ -364,7 +568,7 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
         (p->max_epochs > 0 && !d_schedule))
         return OPS_E_BADARG;
     LaunchPlan pl;
-    rc = plan_launch(k, B, &pl);
+    rc = plan_launch(k, B, p->solver, &pl);
     if (rc) return rc;
     const size_t need = 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
     if (workspace_bytes < need) return OPS_E_WORKSPACE;
@@ -383,6 +587,14 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
     cudaError_t e = cudaMemsetAsync(q.counter, 0, 256, stream);
     if (e != cudaSuccess) return (int)e;
 
+    if (pl.flex) {
+        e = cudaFuncSetAttribute(beamopt_flex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)pl.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        beamopt_flex_kernel<<<pl.blocks, pl.threads, pl.smem_bytes, stream>>>(k, (long long)B, q, pl.lay);
+        e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     const int mf = p->max_forces <= 4 ? 4 : 8;
 #define OPS_LAUNCH(MAXF, SMEM)                                                                      \
     do {                                                                                            \
@@ -420,16 +632,25 @@ int ops_beamsolve_launch(const OpsBeamOptParams *p, int64_t B,
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return (int)e;
+    SolvePtrs q;
+    q.fixed_uy = fixed_uy; q.force_nodes = force_nodes; q.force_vals = force_vals; q.L = L; q.I = I_f64;
+    q.defl = deflections; q.rot = rotations; q.shear = shear; q.moment = moment; q.status = status;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (p->solver == OPS_SOLVER_THREE_MOMENT) {
+        const int threads = 64;
+        const size_t smem = (size_t)threads * (FlexStore::NUM_DOUBLES * 8 + FlexStore::NUM_INTS * 4);
+        e = cudaFuncSetAttribute(beamsolve_flex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        beamsolve_flex_kernel<<<(int)((B + threads - 1) / threads), threads, smem, stream>>>(k, (long long)B, q);
+        e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     const size_t pb = (size_t)5 * k.nn * 8;
     int threads = 32;
     while (threads > 1 && threads * pb > (size_t)smem_optin) threads >>= 1;
     if (threads * pb > (size_t)smem_optin) return OPS_E_UNSUPP;
     const size_t smem = threads * pb;
     const int blocks = (int)((B + threads - 1) / threads);
-    SolvePtrs q;
-    q.fixed_uy = fixed_uy; q.force_nodes = force_nodes; q.force_vals = force_vals; q.L = L; q.I = I_f64;
-    q.defl = deflections; q.rot = rotations; q.shear = shear; q.moment = moment; q.status = status;
-    cudaStream_t stream = (cudaStream_t)cuda_stream;
     const int mf = p->max_forces <= 4 ? 4 : 8;
     if (mf == 4) {
         auto kern = beamsolve_kernel<4>;

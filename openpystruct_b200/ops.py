@@ -14,7 +14,8 @@ import torch
 from . import _cabi
 from .params import BeamOptParams
 
-_INT_FIELDS = ("num_nodes", "num_cases", "max_forces", "max_epochs", "patience", "early_stop", "zero_last_node")
+_INT_FIELDS = ("num_nodes", "num_cases", "max_forces", "max_epochs", "patience", "early_stop", "zero_last_node",
+               "solver")
 _F64_FIELDS = ("E", "G", "udl", "I0", "lr", "gamma", "alpha_moment", "alpha_shear", "tolerance",
                "shear_k", "bending_eps", "clamp_min", "beta1", "beta2", "adam_eps")
 

@@ -30,6 +30,7 @@ class BeamOptParams:
     zero_last_node: bool = False     # MultiCore:222-223 writes 0.0 for the last node
     num_cases: int = 1               # load cases sharing one I vector (reference: 1)
     max_forces: int = 4              # M_forces_max (BeamOpt: 5)
+    solver: int = 0                  # 0 = three-moment (default), 1 = banded LDL^T (OPS_SOLVER_*)
 
     @property
     def G(self) -> float:            # shear modulus, SingleCore:22

@@ -20,7 +20,8 @@ class Params(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("num_nodes", C.c_int32), ("num_cases", C.c_int32),
         ("max_forces", C.c_int32), ("max_epochs", C.c_int32), ("patience", C.c_int32),
-        ("early_stop", C.c_int32), ("zero_last_node", C.c_int32),
+        ("early_stop", C.c_int32), ("zero_last_node", C.c_int32), ("solver", C.c_int32),
+        ("reserved", C.c_int32),
         ("E", C.c_double), ("G", C.c_double), ("udl", C.c_double), ("I0", C.c_double),
         ("lr", C.c_double), ("gamma", C.c_double), ("alpha_moment", C.c_double),
         ("alpha_shear", C.c_double), ("tolerance", C.c_double), ("shear_k", C.c_double),
@@ -34,7 +35,7 @@ def make_params(*, num_nodes=101, num_cases=1, max_forces=4, max_epochs=600, pat
                 alpha_moment=1e-2, alpha_shear=1e-2, tolerance=5e-3, shear_k=0.03, bending_eps=1e-6,
                 clamp_min=1e-8, beta1=0.9, beta2=0.999, adam_eps=1e-8) -> Params:
     return Params(C.sizeof(Params), num_nodes, num_cases, max_forces, max_epochs, patience,
-                  int(early_stop), int(zero_last_node), E, E / (2 * (1 + nu)), udl, I0, lr, gamma,
+                  int(early_stop), int(zero_last_node), 0, 0, E, E / (2 * (1 + nu)), udl, I0, lr, gamma,
                   alpha_moment, alpha_shear, tolerance, shear_k, bending_eps, clamp_min, beta1, beta2, adam_eps)
 
 

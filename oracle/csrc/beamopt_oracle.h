@@ -18,6 +18,8 @@ typedef struct OracleBeamOptParams {
     int32_t patience;
     int32_t early_stop;      /* 0 = run exactly max_epochs */
     int32_t zero_last_node;  /* MultiCore:222-223 */
+    int32_t solver;          /* ignored by the oracle (product-side selection) */
+    int32_t reserved;
     double E, G, udl, I0, lr, gamma, alpha_moment, alpha_shear, tolerance;
     double shear_k, bending_eps, clamp_min, beta1, beta2, adam_eps;
 } OracleBeamOptParams;

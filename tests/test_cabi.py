@@ -41,7 +41,7 @@ def test_exports_every_declared_symbol():
 
 def test_version_and_struct_layout():
     assert "sm_100a" in _cabi.version()
-    assert C.sizeof(_cabi.OpsBeamOptParams) == 8 * 4 + 15 * 8
+    assert C.sizeof(_cabi.OpsBeamOptParams) == 10 * 4 + 15 * 8
     assert C.sizeof(_cabi.OpsBeamOptParams) == C.sizeof(c_oracle.Params)
 
 
