@@ -328,7 +328,7 @@ def run_ours(args):
                                     f"nominal {NOMINAL_FP64_TFLOPS:.1f} TFLOP/s = 148 SM x 64 DFMA/clk x 1.965 GHz; "
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
-                     "kernel": "beamopt_kernel", "kernel_ms": kernel_ms,
+                     "kernel": "beamopt_lanes_kernel<13,100>", "kernel_ms": kernel_ms,
                      "flop_per_beam_iteration": F64_FLOP_PER_ITER,
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_achieved / hbm_peak, "bytes_per_beam": BYTES_PER_BEAM,

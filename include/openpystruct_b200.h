@@ -39,11 +39,14 @@ extern "C" {
 /* per-beam status[] values */
 #define OPS_STATUS_OK          0
 #define OPS_STATUS_SINGULAR    1   /* mechanism / non-SPD pivot / non-finite result: drop the sample */
-#define OPS_STATUS_UNSUPPORTED 3   /* OPS_SOLVER_THREE_MOMENT only: more than 5 rollers; use OPS_SOLVER_BAND_LDLT */
+#define OPS_STATUS_UNSUPPORTED 3   /* OPS_SOLVER_THREE_MOMENT* only: more than 5 rollers; use OPS_SOLVER_BAND_LDLT */
 
 /* solver selection */
-#define OPS_SOLVER_THREE_MOMENT 0  /* exact Schur complement of K onto the support moments (default, fastest) */
+#define OPS_SOLVER_THREE_MOMENT 0  /* exact Schur complement of K onto the support moments (default, fastest):
+                                      eight lanes per beam with the optimiser state in registers for
+                                      num_nodes <= 169, else the thread-per-beam form */
 #define OPS_SOLVER_BAND_LDLT    1  /* in-place banded (block) LDL^T of K, factor kept in shared memory */
+#define OPS_SOLVER_THREE_MOMENT_THREAD 2  /* three-moment, one thread per beam (any num_nodes) */
 
 /* Module-level constants of the reference generators (SingleCore:20-49, MultiCore:20-52, GPU:21-56,
  * BeamOpt:24-48) plus the literals of the loss (SingleCore:195-196) and torch's Adam defaults. */
@@ -154,6 +157,16 @@ int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
  * Synchronises the stream.
  */
 int ops_fp64_peak_probe(int iters, double *tflops, float *elapsed_ms, void *cuda_stream);
+
+/*
+ * Diagnostic (no reference counterpart): checks the branch-free fp32 division / square-root
+ * sequences of the production kernel (csrc/fastmath.cuh) against the compiler's IEEE `/` and sqrtf
+ * on `samples` random operands inside the ranges the kernel guarantees.  mismatches3 receives the
+ * number of results that are not bit-identical {a/b, sqrt(x), 1/b}; rcp64_max_rel_err the largest
+ * |x * rcp64(x) - 1| of the FP64 reciprocal.  Synchronises the stream.
+ */
+int ops_fastmath_selftest(int64_t samples, int64_t *mismatches3, int64_t *samples_run, double *rcp64_max_rel_err,
+                          void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ _lib = None
 EXPORTS = (
     "ops_beamopt_version", "ops_device_count", "ops_set_device", "ops_beamopt_fill_schedule",
     "ops_beamopt_workspace_bytes", "ops_beamopt_launch", "ops_beamsolve_launch", "ops_beamopt_run_host",
-    "ops_fp64_peak_probe",
+    "ops_fp64_peak_probe", "ops_fastmath_selftest",
 )
 
 
@@ -67,6 +67,8 @@ def lib():
         L.ops_beamopt_run_host.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 12 + \
             [C.c_int, C.POINTER(C.c_float)]
         L.ops_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p]
+        L.ops_fastmath_selftest.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_double), C.c_void_p]
         _lib = L
     return _lib
 
@@ -122,3 +124,12 @@ def fp64_peak_probe(iters: int = 1 << 16, stream: int = 0):
     tf, ms = C.c_double(0.0), C.c_float(0.0)
     check(lib().ops_fp64_peak_probe(iters, C.byref(tf), C.byref(ms), stream), "ops_fp64_peak_probe")
     return float(tf.value), float(ms.value)
+
+
+def fastmath_selftest(samples: int = 1 << 26, stream: int = 0) -> dict:
+    """Bit-compare the kernel's branch-free fp32 div/sqrt with the IEEE operators on the device."""
+    mism = (C.c_int64 * 3)()
+    ran, worst = C.c_int64(0), C.c_double(0.0)
+    check(lib().ops_fastmath_selftest(samples, mism, C.byref(ran), C.byref(worst), stream), "ops_fastmath_selftest")
+    return {"div": int(mism[0]), "sqrt": int(mism[1]), "rcp": int(mism[2]), "samples": int(ran.value),
+            "rcp64_max_rel_err": float(worst.value)}

@@ -60,10 +60,23 @@ struct FlexBeam {
     int m;                  // spans between supports (supports = m + 1); m = 0 -> mechanism
     int last;               // node of the last support
     int nloads;             // point loads on free nodes
-    double Le, kc6, wl, wl2h, corr;   // Le, Le/(6E), w*Le, w*Le^2/2, w*Le^2/4
+    double Le, invLe, kc6, wl, wl2h, corr;   // Le, 1/Le, Le/(6E), w*Le, w*Le^2/2, w*Le^2/4
     double Moh, Qoh;        // overhang: moment over / shear just right of the last support
     double EIk;             // Le/E
 };
+
+// Element-length dependent constants of a beam (pure arithmetic on L).
+OPS_HD void flex_geometry(const BeamConsts &k, double L, FlexBeam &fb)
+{
+    const double Le = L / (double)k.n;
+    fb.Le = Le;
+    fb.invLe = 1.0 / Le;
+    fb.kc6 = Le / (6.0 * k.E);
+    fb.EIk = Le / k.E;
+    fb.wl = k.udl * Le;
+    fb.wl2h = 0.5 * k.udl * Le * Le;
+    fb.corr = 0.25 * k.udl * Le * Le;
+}
 
 // One-time (per beam) set-up of the I-independent data.  fixed(i): uy_i constrained (node 0 implied).
 // Returns 0 ok, 1 mechanism (no roller), 3 more supports than FLEX_MAXS.
@@ -72,13 +85,8 @@ OPS_HD int flex_setup(const BeamConsts &k, double L, FixedFn fixed, int nforces,
                       const double *fval, const FlexStore &fs, FlexBeam &fb)
 {
     const int n = k.n;
-    const double Le = L / (double)n;
-    fb.Le = Le;
-    fb.kc6 = Le / (6.0 * k.E);
-    fb.EIk = Le / k.E;
-    fb.wl = k.udl * Le;
-    fb.wl2h = 0.5 * k.udl * Le * Le;
-    fb.corr = 0.25 * k.udl * Le * Le;
+    flex_geometry(k, L, fb);
+    const double Le = fb.Le;
     // supports, ascending
     int m = 0;
     fs.sup(0) = 0;

@@ -1,0 +1,46 @@
+// Declarations shared by the translation units of libopenpystruct_b200.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "beamopt_core.cuh"
+
+namespace ops {
+
+// device pointers of one ops_beamopt_launch call (include/openpystruct_b200.h documents the arrays)
+struct OptPtrs {
+    const uint8_t *fixed_uy;
+    const int32_t *force_nodes;
+    const double *force_vals;
+    const double *L;
+    const float *sched;
+    float *I_values;
+    double *defl, *rot;
+    float *shear, *moment;
+    int32_t *epochs;
+    float *loss;
+    int32_t *status;
+    unsigned long long *counter;
+    double *ws_d;      // global scratch (thread-per-beam kernels only)
+    float *ws_f;
+    uint32_t *ws_mask;
+};
+
+// eight-lanes-per-beam three-moment kernel (beamopt_lanes.cu)
+struct LanesPlan {
+    int epl;             // element slots per lane (template instance)
+    int nfix;            // compile-time element count of the instance (0 = run-time n)
+    int threads, blocks;
+    size_t smem_bytes;
+};
+bool lanes_supported(const BeamConsts &k);
+int lanes_plan(const BeamConsts &k, int64_t B, int sms, int smem_optin, LanesPlan *pl);
+cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream);
+
+// fastmath.cuh against the compiler's IEEE operators; out4 = {div mismatches, sqrt mismatches,
+// reciprocal mismatches, samples}
+cudaError_t fastmath_selftest(long long samples, unsigned long long *host_out4, double *worst_rcp64,
+                              cudaStream_t stream);
+
+}  // namespace ops

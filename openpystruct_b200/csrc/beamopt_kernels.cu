@@ -18,28 +18,11 @@
 #include "../../include/openpystruct_b200.h"
 #include "beamopt_core.cuh"
 #include "beamopt_flex.cuh"
+#include "beamopt_internal.cuh"
 
 #define OPS_VERSION "openpystruct_b200 0.1.0 sm_100a"
 
 namespace ops {
-
-struct OptPtrs {
-    const uint8_t *fixed_uy;
-    const int32_t *force_nodes;
-    const double *force_vals;
-    const double *L;
-    const float *sched;
-    float *I_values;
-    double *defl, *rot;
-    float *shear, *moment;
-    int32_t *epochs;
-    float *loss;
-    int32_t *status;
-    unsigned long long *counter;
-    double *ws_d;      // global scratch (only when !SMEM)
-    float *ws_f;
-    uint32_t *ws_mask;
-};
 
 // fixed-uy bitmask words per beam, laid out [word][thread]
 struct MaskStore {
@@ -361,7 +344,9 @@ static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
     if (p->num_nodes < 2 || p->num_cases < 1 || p->max_forces < 0 || p->max_epochs < 0) return OPS_E_BADARG;
     if (p->num_cases != 1) return OPS_E_UNSUPP;
     if (p->max_forces > 8) return OPS_E_UNSUPP;
-    if (p->solver != OPS_SOLVER_THREE_MOMENT && p->solver != OPS_SOLVER_BAND_LDLT) return OPS_E_BADARG;
+    if (p->solver != OPS_SOLVER_THREE_MOMENT && p->solver != OPS_SOLVER_BAND_LDLT &&
+        p->solver != OPS_SOLVER_THREE_MOMENT_THREAD)
+        return OPS_E_BADARG;
     if (p->reserved != 0) return OPS_E_BADARG;
     k->nn = p->num_nodes;
     k->n = p->num_nodes - 1;
@@ -389,7 +374,9 @@ static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
 }
 
 struct LaunchPlan {
-    bool flex;           // three-moment kernel
+    bool lanes;          // eight-lanes-per-beam three-moment kernel (beamopt_lanes.cu)
+    LanesPlan lp;
+    bool flex;           // thread-per-beam three-moment kernel
     FlexLayout lay;
     bool smem;
     int threads;         // per CTA
@@ -456,7 +443,13 @@ static int plan_launch(const BeamConsts &k, int64_t B, int solver, LaunchPlan *p
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return (int)e;
-    if (solver == OPS_SOLVER_THREE_MOMENT) return plan_flex(k, B, sms, smem_optin, pl);
+    if (solver == OPS_SOLVER_THREE_MOMENT && lanes_supported(k)) {
+        memset(pl, 0, sizeof *pl);
+        pl->lanes = true;
+        return lanes_plan(k, B, sms, smem_optin, &pl->lp);
+    }
+    if (solver == OPS_SOLVER_THREE_MOMENT || solver == OPS_SOLVER_THREE_MOMENT_THREAD)
+        return plan_flex(k, B, sms, smem_optin, pl);
     const size_t pb = per_beam_bytes(k.nn);
     memset(pl, 0, sizeof *pl);
     // experiment knobs (profiling only): OPS_BEAMOPT_GLOBAL=1 forces the global-scratch variant,
@@ -587,6 +580,10 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
     cudaError_t e = cudaMemsetAsync(q.counter, 0, 256, stream);
     if (e != cudaSuccess) return (int)e;
 
+    if (pl.lanes) {
+        e = lanes_launch(k, (long long)B, q, pl.lp, stream);
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     if (pl.flex) {
         e = cudaFuncSetAttribute(beamopt_flex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl.smem_bytes);
@@ -636,7 +633,7 @@ int ops_beamsolve_launch(const OpsBeamOptParams *p, int64_t B,
     q.fixed_uy = fixed_uy; q.force_nodes = force_nodes; q.force_vals = force_vals; q.L = L; q.I = I_f64;
     q.defl = deflections; q.rot = rotations; q.shear = shear; q.moment = moment; q.status = status;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (p->solver == OPS_SOLVER_THREE_MOMENT) {
+    if (p->solver == OPS_SOLVER_THREE_MOMENT || p->solver == OPS_SOLVER_THREE_MOMENT_THREAD) {
         const int threads = 64;
         const size_t smem = (size_t)threads * (FlexStore::NUM_DOUBLES * 8 + FlexStore::NUM_INTS * 4);
         e = cudaFuncSetAttribute(beamsolve_flex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -694,6 +691,18 @@ int ops_fp64_peak_probe(int iters, double *tflops, float *elapsed_ms, void *cuda
     const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
     *tflops = flops / ((double)ms * 1e-3) / 1e12;
     if (elapsed_ms) *elapsed_ms = ms;
+    return 0;
+}
+
+int ops_fastmath_selftest(int64_t samples, int64_t *mismatches3, int64_t *samples_run, double *rcp64_max_rel_err,
+                          void *cuda_stream)
+{
+    if (samples <= 0 || !mismatches3 || !samples_run || !rcp64_max_rel_err) return OPS_E_BADARG;
+    unsigned long long out[4] = {0, 0, 0, 0};
+    cudaError_t e = fastmath_selftest((long long)samples, out, rcp64_max_rel_err, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    mismatches3[0] = (int64_t)out[0]; mismatches3[1] = (int64_t)out[1]; mismatches3[2] = (int64_t)out[2];
+    *samples_run = (int64_t)out[3];
     return 0;
 }
 

@@ -1,0 +1,267 @@
+// sm_100a kernel of the production iteration: eight lanes per beam, persistent groups.
+//
+// One CTA per SM; a CTA is T/8 independent 8-lane groups, four per warp.  A group that finishes its
+// beam (early stop, SingleCore:211-219, or max_e epochs) pulls the next beam index from a global
+// counter, so ragged stopping never idles a group.  Phases of a group are separated by
+// __syncwarp(group mask); nothing crosses warps, nothing but the beam's inputs (read once) and its
+// record (written once) crosses HBM.  Arithmetic: beamopt_lanes.cuh.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (one IEEE rounding per written op).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "beamopt_internal.cuh"
+#include "beamopt_lanes.cuh"
+
+namespace ops {
+
+using namespace lanes;
+
+constexpr int LANES_MAX_THREADS = 320;
+
+template <int EPL, int NFIX>
+__global__ void __launch_bounds__(LANES_MAX_THREADS, 1)
+beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = blockDim.x, G = T / LPB;
+    const int tid = threadIdx.x, l = tid & (LPB - 1), g = tid / LPB;
+    const unsigned gmask = 0xffu << (tid & 24);
+    const int n = NFIX ? NFIX : k.n;
+    const int nn = n + 1;
+
+    double *lane_d = reinterpret_cast<double *>(smem_raw);
+    double *grp_d = lane_d + (size_t)lane_doubles(EPL) * T;
+    int *grp_i = reinterpret_cast<int *>(grp_d + (size_t)GROUP_DOUBLES * G);
+    LaneStore ls;
+    ls.ls = T;
+    ls.gc = lane_d + tid;
+    ls.qc = ls.gc + (size_t)EPL * T;
+    ls.m0 = ls.qc + (size_t)EPL * T;
+    ls.q0 = ls.m0 + (size_t)EPL * T;
+    ls.scr = ls.q0 + (size_t)EPL * T;
+    GroupStore gs;
+    gs.gs = G;
+    gs.fs.sd = grp_d + g;
+    gs.fs.stride = G;
+    gs.tab = gs.fs.sd + (size_t)FlexStore::NUM_DOUBLES * G;
+    gs.gd = gs.tab + (size_t)TAB_SLOTS * G;
+    gs.fs.si = grp_i + g;
+    gs.gi = gs.fs.si + (size_t)FlexStore::NUM_INTS * G;
+
+    LaneRegs<EPL> rg;
+    FlexBeam fb;
+    long long b = -1;
+    bool have = false, exhausted = false;
+    int t = 0, counter = 0, bad = 0;
+    double best = INFINITY;
+    float lossf = NAN;
+
+    while (true) {
+        if (!have && !exhausted) {
+            long long nb = 0;
+            if (l == 0) nb = (long long)atomicAdd(p.counter, 1ULL);
+            nb = __shfl_sync(gmask, nb, 0, LPB);
+            if (nb < B) {
+                b = nb;
+                have = true;
+                t = 0; counter = 0; best = INFINITY; lossf = NAN;
+                if (l == 0) {
+                    int fnode[FLEX_MAXF];
+                    double fval[FLEX_MAXF];
+                    for (int j = 0; j < k.max_forces; ++j) {
+                        fnode[j] = p.force_nodes[b * k.max_forces + j];
+                        fval[j] = p.force_vals[b * k.max_forces + j];
+                    }
+                    const uint8_t *fx = p.fixed_uy + b * nn;
+                    FlexBeam f0;
+                    const int rc = flex_setup(k, p.L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode,
+                                              fval, gs.fs, f0);
+                    group_publish(f0, rc, gs);
+                }
+                __syncwarp(gmask);
+                bad = group_fetch(k, p.L[b], gs, fb);
+                if (!bad) lane_init<EPL>(k, n, fb, gs, ls, l, rg);
+                else lane_reset<EPL>(k, rg);
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            bool done = (k.max_epochs <= 0) || (bad != 0);
+            float neg_step = 0.0f, bc2_sqrt = 1.0f;
+            if (!done) {
+                neg_step = __ldg(p.sched + 2 * t);
+                bc2_sqrt = __ldg(p.sched + 2 * t + 1);
+                lane_pass1<EPL>(rg, ls);
+                __syncwarp(gmask);
+                lane_reduce(l, ls, gs);
+                __syncwarp(gmask);
+                const int rc = group_solve(fb, gs, l);
+                __syncwarp(gmask);
+                lane_forces<EPL>(k, n, rg, ls, gs, l);
+                __syncwarp(gmask);
+                lossf = group_loss(k, n, ls, l);
+                ++t;
+                if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
+                if (k.early_stop) {
+                    const double lv = (double)lossf;
+                    if (lv < best - k.tol) { best = lv; counter = 0; } else { ++counter; }
+                    if (counter >= k.patience) done = true;
+                }
+                if (t >= k.max_epochs) done = true;
+            }
+            if (!done) {
+                lane_adam<EPL>(k, rg, neg_step, bc2_sqrt);
+            } else {
+                // record of the beam: fields of the last analysed inertias, then the last Adam step
+                const bool fields = (t > 0) && (bad == 0);
+                lane_emit_forces<EPL>(n, rg, ls, gs, l, fields, p.shear + b * n, p.moment + b * n);
+                __syncwarp(gmask);
+                if (l == 0) {
+                    LaneStore ls0 = ls;
+                    group_emit_displacements(k, fb, ls0, gs, fields, p.defl + b * nn, p.rot + b * nn);
+                    p.epochs[b] = t;
+                    p.loss[b] = lossf;
+                    p.status[b] = bad;
+                }
+                if (t > 0) lane_adam<EPL>(k, rg, neg_step, bc2_sqrt);
+                lane_emit_inertias<EPL>(n, rg, l, p.I_values + b * n);
+                __syncwarp(gmask);
+                have = false;
+            }
+        }
+    }
+}
+
+bool lanes_supported(const BeamConsts &k)
+{
+    return k.n >= 1 && k.n <= 8 * 21 && k.max_forces <= FLEX_MAXF;
+}
+
+static int pick_epl(int n)
+{
+    if (n <= 32) return 4;
+    if (n <= 64) return 8;
+    if (n <= 104) return 13;
+    return 21;
+}
+
+int lanes_plan(const BeamConsts &k, int64_t B, int sms, int smem_optin, LanesPlan *pl)
+{
+    pl->epl = pick_epl(k.n);
+    pl->nfix = (k.n == 100) ? 100 : 0;
+    const size_t per_group = (size_t)LPB * 8 * lane_doubles(pl->epl) + (size_t)GROUP_DOUBLES * 8 + (size_t)GROUP_INTS * 4;
+    int groups = (int)((size_t)smem_optin / per_group);
+    int T = groups * LPB / 32 * 32;
+    if (T > LANES_MAX_THREADS) T = LANES_MAX_THREADS;
+    const char *thr_env = getenv("OPS_LANES_THREADS");            // profiling knob
+    if (thr_env && atoi(thr_env) >= 32 && atoi(thr_env) <= T) T = atoi(thr_env) / 32 * 32;
+    if (T < 32) return -2;
+    pl->threads = T;
+    pl->smem_bytes = per_group * (T / LPB);
+    const long per_cta = T / LPB;
+    long want = (long)((B + per_cta - 1) / per_cta);
+    pl->blocks = (int)(want < sms ? want : sms);
+    if (pl->blocks < 1) pl->blocks = 1;
+    // spread a batch that does not fill every CTA evenly over all SMs
+    if (pl->blocks < sms && B > pl->blocks) {
+        pl->blocks = (int)(B < sms ? B : sms);
+    }
+    return 0;
+}
+
+template <int EPL, int NFIX>
+static cudaError_t launch_instance(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl,
+                                   cudaStream_t stream)
+{
+    auto kern = beamopt_lanes_kernel<EPL, NFIX>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<pl.blocks, pl.threads, pl.smem_bytes, stream>>>(k, B, p);
+    return cudaGetLastError();
+}
+
+cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream)
+{
+    if (pl.nfix == 100) return launch_instance<13, 100>(k, B, p, pl, stream);
+    switch (pl.epl) {
+    case 4: return launch_instance<4, 0>(k, B, p, pl, stream);
+    case 8: return launch_instance<8, 0>(k, B, p, pl, stream);
+    case 13: return launch_instance<13, 0>(k, B, p, pl, stream);
+    default: return launch_instance<21, 0>(k, B, p, pl, stream);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// self test of fastmath.cuh against the compiler's IEEE operators (ops_fastmath_selftest)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int lcg(unsigned long long &s)
+{
+    s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+    return (unsigned int)(s >> 32);
+}
+
+// random float with a biased exponent in [elo, ehi] and a random mantissa; sign positive
+__device__ __forceinline__ float rand_float(unsigned long long &s, int elo, int ehi)
+{
+    const unsigned int m = lcg(s) & 0x7fffffu;
+    const unsigned int e = (unsigned int)elo + lcg(s) % (unsigned int)(ehi - elo + 1);
+    return __uint_as_float((e << 23) | m);
+}
+
+__global__ void fastmath_selftest_kernel(int per_thread, unsigned long long seed, unsigned long long *out)
+{
+    unsigned long long s = seed + 0x9E3779B97F4A7C15ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned long long bad_div = 0, bad_sqrt = 0, bad_rcp = 0;
+    double worst = 0.0;
+    for (int i = 0; i < per_thread; ++i) {
+        // division: b in [2^-60, 2^60], a zero or in [2^-60, 2^60]  (quotient within [2^-120, 2^120])
+        const float b = rand_float(s, 67, 187);
+        float a = rand_float(s, 67, 187);
+        if ((lcg(s) & 1023u) == 0) a = 0.0f;
+        if (lcg(s) & 1u) a = -a;
+        const float r = fm::rcp_r(b);
+        if (__float_as_uint(fm::div_r(a, b, r)) != __float_as_uint(a / b)) ++bad_div;
+        if (__float_as_uint(fm::div_f(1.0f, b)) != __float_as_uint(1.0f / b)) ++bad_rcp;
+        // square root: x in [2^-101, 2^127]
+        const float x = rand_float(s, 26, 254);
+        if (__float_as_uint(fm::sqrt_f(x)) != __float_as_uint(sqrtf(x))) ++bad_sqrt;
+        // fp64 reciprocal of an fp32-valued argument in [2^-40, 2^40]
+        const double xd = (double)rand_float(s, 87, 167);
+        const double e = fabs(fm::rcp64(xd) * xd - 1.0);
+        worst = e > worst ? e : worst;
+    }
+    atomicAdd(out + 0, bad_div);
+    atomicAdd(out + 1, bad_sqrt);
+    atomicAdd(out + 2, bad_rcp);
+    atomicMax(out + 3, (unsigned long long)__double_as_longlong(worst));
+}
+
+cudaError_t fastmath_selftest(long long samples, unsigned long long *host_out4, double *worst_rcp64, cudaStream_t stream)
+{
+    unsigned long long *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, 32);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(d, 0, 32, stream);
+    const int threads = 256, blocks = 592;
+    int per_thread = (int)(samples / ((long long)threads * blocks)) + 1;
+    fastmath_selftest_kernel<<<blocks, threads, 0, stream>>>(per_thread, 0x1234567ULL, d);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out4, d, 32, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return e;
+    long long bits = (long long)host_out4[3];
+    double w;
+    memcpy(&w, &bits, 8);
+    *worst_rcp64 = w;
+    host_out4[3] = (unsigned long long)per_thread * threads * blocks;
+    return cudaSuccess;
+}
+
+}  // namespace ops

@@ -211,3 +211,110 @@ extern "C" int hostsim_beamsolve_flex(const OpsBeamOptParams *p, int64_t B, cons
     }
     return 0;
 }
+
+// Eight-lanes-per-beam production iteration (beamopt_lanes.cuh) with the control flow of
+// beamopt_lanes_kernel: the phase functions are the device code itself, run lane by lane; the
+// __syncwarp points of the kernel are the boundaries between the lane loops.
+#include "../../openpystruct_b200/csrc/beamopt_lanes.cuh"
+
+template <int EPL>
+static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, const int32_t *force_nodes,
+                     const double *force_vals, const double *L, const float *sched, float *I_values,
+                     double *defl, double *rot, float *shear, float *moment, int32_t *epochs, float *loss,
+                     int32_t *status)
+{
+    using namespace ops::lanes;
+    const int n = k.n, nn = k.nn;
+    std::vector<double> lane_d((size_t)lane_doubles(EPL) * LPB), grp_d(GROUP_DOUBLES);
+    std::vector<int> grp_i(GROUP_INTS);
+    LaneStore ls[LPB];
+    for (int l = 0; l < LPB; ++l) {
+        ls[l].ls = LPB;
+        ls[l].gc = lane_d.data() + l;
+        ls[l].qc = ls[l].gc + (size_t)EPL * LPB;
+        ls[l].m0 = ls[l].qc + (size_t)EPL * LPB;
+        ls[l].q0 = ls[l].m0 + (size_t)EPL * LPB;
+        ls[l].scr = ls[l].q0 + (size_t)EPL * LPB;
+    }
+    GroupStore gs;
+    gs.gs = 1;
+    gs.fs.sd = grp_d.data(); gs.fs.stride = 1;
+    gs.tab = gs.fs.sd + FlexStore::NUM_DOUBLES;
+    gs.gd = gs.tab + TAB_SLOTS;
+    gs.fs.si = grp_i.data();
+    gs.gi = gs.fs.si + FlexStore::NUM_INTS;
+    for (int64_t b = 0; b < B; ++b) {
+        LaneRegs<EPL> rg[LPB];
+        FlexBeam fb;
+        int fnode[FLEX_MAXF];
+        double fval[FLEX_MAXF];
+        for (int j = 0; j < k.max_forces; ++j) {
+            fnode[j] = force_nodes[b * k.max_forces + j];
+            fval[j] = force_vals[b * k.max_forces + j];
+        }
+        const uint8_t *fx = fixed_uy + b * nn;
+        {
+            FlexBeam f0;
+            const int rc = flex_setup(k, L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode, fval, gs.fs, f0);
+            group_publish(f0, rc, gs);
+        }
+        int bad = group_fetch(k, L[b], gs, fb);
+        for (int l = 0; l < LPB; ++l) {
+            if (!bad) lane_init<EPL>(k, n, fb, gs, ls[l], l, rg[l]);
+            else lane_reset<EPL>(k, rg[l]);
+        }
+        int t = 0, counter = 0;
+        double best = INFINITY;
+        float lossf = NAN, neg_step = 0.0f, bc2_sqrt = 1.0f;
+        bool done = (k.max_epochs <= 0) || bad;
+        while (!done) {
+            neg_step = sched[2 * t]; bc2_sqrt = sched[2 * t + 1];
+            for (int l = 0; l < LPB; ++l) lane_pass1<EPL>(rg[l], ls[l]);
+            for (int l = 0; l < LPB; ++l) lane_reduce(l, ls[l], gs);
+            int rc = 0;
+            for (int l = LPB - 1; l >= 0; --l) rc = group_solve(fb, gs, l);
+            for (int l = 0; l < LPB; ++l) lane_forces<EPL>(k, n, rg[l], ls[l], gs, l);
+            float lv[LPB];
+            for (int l = 0; l < LPB; ++l) lv[l] = group_loss(k, n, ls[l], l);
+            for (int l = 1; l < LPB; ++l) if (memcmp(&lv[l], &lv[0], 4) != 0) return -100;   // lanes must agree
+            lossf = lv[0];
+            ++t;
+            if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
+            if (k.early_stop) {
+                const double l_ = (double)lossf;
+                if (l_ < best - k.tol) { best = l_; counter = 0; } else { ++counter; }
+                if (counter >= k.patience) done = true;
+            }
+            if (t >= k.max_epochs) done = true;
+            if (!done) for (int l = 0; l < LPB; ++l) lane_adam<EPL>(k, rg[l], neg_step, bc2_sqrt);
+        }
+        const bool fields = (t > 0) && (bad == 0);
+        for (int l = 0; l < LPB; ++l)
+            lane_emit_forces<EPL>(n, rg[l], ls[l], gs, l, fields, shear + b * n, moment + b * n);
+        group_emit_displacements(k, fb, ls[0], gs, fields, defl + b * nn, rot + b * nn);
+        epochs[b] = t; loss[b] = lossf; status[b] = bad;
+        for (int l = 0; l < LPB; ++l) {
+            if (t > 0) lane_adam<EPL>(k, rg[l], neg_step, bc2_sqrt);
+            lane_emit_inertias<EPL>(n, rg[l], l, I_values + b * n);
+        }
+    }
+    return 0;
+}
+
+extern "C" int hostsim_beamopt_lanes(const OpsBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
+                                     const int32_t *force_nodes, const double *force_vals, const double *L,
+                                     const float *sched, float *I_values, double *defl, double *rot,
+                                     float *shear, float *moment, int32_t *epochs, float *loss, int32_t *status)
+{
+    if (p->num_cases != 1 || p->max_forces > FLEX_MAXF) return OPS_E_UNSUPP;
+    BeamConsts k;
+    consts_from(p, &k);
+#define RUN(EPL) lanes_run<EPL>(k, B, fixed_uy, force_nodes, force_vals, L, sched, I_values, defl, rot, shear, \
+                                moment, epochs, loss, status)
+    if (k.n <= 32) return RUN(4);
+    if (k.n <= 64) return RUN(8);
+    if (k.n <= 104) return RUN(13);
+    if (k.n <= 168) return RUN(21);
+#undef RUN
+    return OPS_E_UNSUPP;
+}
