@@ -34,21 +34,20 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     const int nn = n + 1;
 
     double *lane_d = reinterpret_cast<double *>(smem_raw);
-    double *grp_d = lane_d + (size_t)lane_doubles(EPL) * T;
+    double *tab_d = lane_d + (size_t)lane_doubles(EPL) * T;
+    double *grp_d = tab_d + (size_t)TAB_SLOTS * G;
     int *grp_i = reinterpret_cast<int *>(grp_d + (size_t)GROUP_DOUBLES * G);
     LaneStore ls;
     ls.ls = T;
-    ls.gc = lane_d + tid;
-    ls.qc = ls.gc + (size_t)EPL * T;
-    ls.m0 = ls.qc + (size_t)EPL * T;
-    ls.q0 = ls.m0 + (size_t)EPL * T;
-    ls.scr = ls.q0 + (size_t)EPL * T;
+    ls.gq = reinterpret_cast<Pair *>(lane_d) + tid;
+    ls.mq = ls.gq + (size_t)EPL * T;
+    ls.scr = lane_d + (size_t)4 * EPL * T + tid;
     GroupStore gs;
     gs.gs = G;
+    gs.tab = tab_d + (size_t)TAB_SLOTS * g;
     gs.fs.sd = grp_d + g;
     gs.fs.stride = G;
-    gs.tab = gs.fs.sd + (size_t)FlexStore::NUM_DOUBLES * G;
-    gs.gd = gs.tab + (size_t)TAB_SLOTS * G;
+    gs.gd = gs.fs.sd + (size_t)FlexStore::NUM_DOUBLES * G;
     gs.fs.si = grp_i + g;
     gs.gi = gs.fs.si + (size_t)FlexStore::NUM_INTS * G;
 
@@ -81,11 +80,16 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                     const int rc = flex_setup(k, p.L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode,
                                               fval, gs.fs, f0);
                     group_publish(f0, rc, gs);
+                    group_table_init(gs);
                 }
                 __syncwarp(gmask);
                 bad = group_fetch(k, p.L[b], gs, fb);
-                if (!bad) lane_init<EPL>(k, n, fb, gs, ls, l, rg);
-                else lane_reset<EPL>(k, rg);
+                if (!bad) {
+                    lane_init<EPL>(k, n, fb, gs, ls, l, rg);
+                    lane_pass1<EPL>(rg, ls);
+                } else {
+                    lane_reset<EPL>(k, rg);
+                }
             } else {
                 exhausted = true;
             }
@@ -97,9 +101,8 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             if (!done) {
                 neg_step = __ldg(p.sched + 2 * t);
                 bc2_sqrt = __ldg(p.sched + 2 * t + 1);
-                lane_pass1<EPL>(rg, ls);
                 __syncwarp(gmask);
-                lane_reduce(l, ls, gs);
+                lane_reduce(l, fb.m, ls, gs);
                 __syncwarp(gmask);
                 const int rc = group_solve(fb, gs, l);
                 __syncwarp(gmask);
@@ -116,7 +119,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                 if (t >= k.max_epochs) done = true;
             }
             if (!done) {
-                lane_adam<EPL>(k, rg, neg_step, bc2_sqrt);
+                lane_adam<EPL, true>(k, rg, ls, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
             } else {
                 // record of the beam: fields of the last analysed inertias, then the last Adam step
                 const bool fields = (t > 0) && (bad == 0);
@@ -129,7 +132,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                     p.loss[b] = lossf;
                     p.status[b] = bad;
                 }
-                if (t > 0) lane_adam<EPL>(k, rg, neg_step, bc2_sqrt);
+                if (t > 0) lane_adam<EPL, false>(k, rg, ls, neg_step, bc2_sqrt);
                 lane_emit_inertias<EPL>(n, rg, l, p.I_values + b * n);
                 __syncwarp(gmask);
                 have = false;
@@ -155,7 +158,8 @@ int lanes_plan(const BeamConsts &k, int64_t B, int sms, int smem_optin, LanesPla
 {
     pl->epl = pick_epl(k.n);
     pl->nfix = (k.n == 100) ? 100 : 0;
-    const size_t per_group = (size_t)LPB * 8 * lane_doubles(pl->epl) + (size_t)GROUP_DOUBLES * 8 + (size_t)GROUP_INTS * 4;
+    const size_t per_group = (size_t)LPB * 8 * lane_doubles(pl->epl) + (size_t)(TAB_SLOTS + GROUP_DOUBLES) * 8 +
+                             (size_t)GROUP_INTS * 4;
     int groups = (int)((size_t)smem_optin / per_group);
     int T = groups * LPB / 32 * 32;
     if (T > LANES_MAX_THREADS) T = LANES_MAX_THREADS;
@@ -226,8 +230,11 @@ __global__ void fastmath_selftest_kernel(int per_thread, unsigned long long seed
         if ((lcg(s) & 1023u) == 0) a = 0.0f;
         if (lcg(s) & 1u) a = -a;
         const float r = fm::rcp_r(b);
-        if (__float_as_uint(fm::div_r(a, b, r)) != __float_as_uint(a / b)) ++bad_div;
-        if (__float_as_uint(fm::div_f(1.0f, b)) != __float_as_uint(1.0f / b)) ++bad_rcp;
+        // (a signed zero numerator keeps the magnitude but not the sign: every numerator of the kernel is
+        //  either non-negative or only ever added to a non-zero value)
+        const float qf = fm::div_r(a, b, r), qi = a / b;
+        if (__float_as_uint(qf) != __float_as_uint(qi) && !(qf == 0.0f && qi == 0.0f)) ++bad_div;
+        if (__float_as_uint(fm::rcp_f(b)) != __float_as_uint(1.0f / b)) ++bad_rcp;
         // square root: x in [2^-101, 2^127]
         const float x = rand_float(s, 26, 254);
         if (__float_as_uint(fm::sqrt_f(x)) != __float_as_uint(sqrtf(x))) ++bad_sqrt;

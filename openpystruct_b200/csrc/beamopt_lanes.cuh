@@ -40,10 +40,11 @@ constexpr int DUMMY = NSPAN;                    // span id of overhang elements 
 constexpr int NSUM = 5;                         // R0, R1, R2, G, Q
 constexpr int SCR_STAGE = NSPAN * NSUM;         // 3 slots after the partial sums: {row sum, tail} of sum I, d, q
 constexpr int SCR_SLOTS = SCR_STAGE + 3;
-constexpr int TAB_SLOTS = (NSPAN + 1) * 3;      // per span: MS_l, (MS_r - MS_l) d, (MS_r - MS_l) d / Le
+constexpr int TAB_ROW = 4;                      // per span: MS_l, (MS_r - MS_l) d, (MS_r - MS_l) d / Le, pad
+constexpr int TAB_SLOTS = (NSPAN + 1) * TAB_ROW + 2;   // contiguous per group; +2 keeps four groups on distinct banks
 constexpr int GX_DOUBLES = 2;                   // Moh, Qoh
 constexpr int GX_INTS = 4;                      // m, last, nloads, setup status
-constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + TAB_SLOTS + GX_DOUBLES;
+constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + GX_DOUBLES;   // strided [slot][group] columns (+ TAB_SLOTS contiguous)
 constexpr int GROUP_INTS = FlexStore::NUM_INTS + GX_INTS;
 
 OPS_HD constexpr int lane_doubles(int epl) { return 4 * epl + SCR_SLOTS; }
@@ -52,19 +53,25 @@ template <int EPL>
 struct LaneRegs {
     float I[EPL], m[EPL], v[EPL], g[EPL], ke[EPL];
     unsigned long long spans;                   // 3 bits per slot k: span id of element 8 k + l
+    unsigned int starts, ends;                  // bit k: slot k opens / closes a run of slots of one (real) span
+};
+
+struct alignas(16) Pair {                       // two doubles moved with one 128-bit shared access
+    double x, y;
 };
 
 // per-lane shared columns, entry k at base[k * ls]
 struct LaneStore {
-    double *gc, *qc, *m0, *q0;                  // [EPL]: G and Q coefficients, M0 and Q0 of the element
+    Pair *gq;                                   // [EPL]: {G, Q} coefficients of the element
+    Pair *mq;                                   // [EPL]: {M0, Q0} of the element
     double *scr;                                // [SCR_SLOTS]
     long ls;
 };
 
-// per-group shared columns, entry k at base[k * gs]
+// per-group shared data: strided columns (entry k at base[k * gs]) and the contiguous span table
 struct GroupStore {
-    FlexStore fs;                               // supports, loads, RA, DXI; slots A..Q hold R0, R1, R2, G, Q
-    double *tab;                                // [TAB_SLOTS]
+    FlexStore fs;                               // supports, loads, RA, DXI; slots A..Q hold a, b, c, p, q (no Le/6E)
+    double *tab;                                // [TAB_SLOTS] contiguous, 16-byte aligned
     double *gd;                                 // [GX_DOUBLES]
     int *gi;                                    // [GX_INTS]
     long gs;
@@ -108,6 +115,8 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
     const int m = fb.m, last = fb.last, nl = fb.nloads;
     for (int s = 0; s < SCR_SLOTS; ++s) ls.scr[(long)s * ls.ls] = 0.0;
     unsigned long long spans = 0;
+    unsigned int starts = 0, ends = 0;
+    int prev = -1;
 #pragma unroll
     for (int kk = 0; kk < EPL; ++kk) {
         const int e = LPB * kk + l;
@@ -154,11 +163,19 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
             }
         }
         spans |= (unsigned long long)sp << (3 * kk);
+        if (sp != prev) {
+            starts |= 1u << kk;
+            if (kk > 0 && prev != DUMMY) ends |= 1u << (kk - 1);
+        }
+        prev = sp;
         rg.I[kk] = I0; rg.m[kk] = 0.0f; rg.v[kk] = 0.0f; rg.g[kk] = 0.0f; rg.ke[kk] = (float)kef;
-        ls.gc[(long)kk * ls.ls] = G; ls.qc[(long)kk * ls.ls] = Qc;
-        ls.m0[(long)kk * ls.ls] = M0; ls.q0[(long)kk * ls.ls] = Q0;
+        Pair gq; gq.x = G; gq.y = Qc;
+        Pair mq; mq.x = M0; mq.y = Q0;
+        ls.gq[(long)kk * ls.ls] = gq;
+        ls.mq[(long)kk * ls.ls] = mq;
     }
-    rg.spans = spans;
+    if (prev != DUMMY) ends |= 1u << (EPL - 1);
+    rg.spans = spans; rg.starts = starts; rg.ends = ends;
 }
 
 // a beam rejected at set-up (mechanism / unsupported support count) still emits I_0 in its record
@@ -169,73 +186,72 @@ OPS_HD void lane_reset(const BeamConsts &k, LaneRegs<EPL> &rg)
     for (int kk = 0; kk < EPL; ++kk) {
         rg.I[kk] = k.I0f; rg.m[kk] = 0.0f; rg.v[kk] = 0.0f; rg.g[kk] = 0.0f; rg.ke[kk] = 0.0f;
     }
-    rg.spans = 0;
+    rg.spans = 0; rg.starts = 0; rg.ends = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // per epoch
 // ---------------------------------------------------------------------------------------------
-OPS_HD void flush_span(const LaneStore &ls, int j, double R0, double R1, double R2, double G, double Q)
+// PASS 1: flexibility sums of the lane's elements, one partial per span in the lane's scratch column.
+// The five running sums restart where the lane's slots enter a new span (multiplication by an exact
+// 0/1 factor instead of a branch, so the thirteen element bodies stay one basic block apart from the
+// rare store of a finished partial).
+struct SpanSums {
+    double R0, R1, R2, G, Q;
+};
+
+template <int EPL>
+OPS_HD void pass1_element(const LaneRegs<EPL> &rg, const LaneStore &ls, int kk, SpanSums &a)
 {
-    double *s = ls.scr + (long)(j * NSUM) * ls.ls;
-    s[0] = R0; s[ls.ls] = R1; s[2 * ls.ls] = R2; s[3 * ls.ls] = G; s[4 * ls.ls] = Q;
+    const double keep = ((rg.starts >> kk) & 1u) ? 0.0 : 1.0;
+    const double r = fm::rcp64((double)rg.I[kk]);
+    const double ke = (double)rg.ke[kk];
+    const Pair gq = ls.gq[(long)kk * ls.ls];
+    const double t = r * ke;
+    a.R0 = fma(a.R0, keep, r);
+    a.R1 = fma(a.R1, keep, t);
+    a.R2 = fma(t, ke, a.R2 * keep);
+    a.G = fma(r, gq.x, a.G * keep);
+    a.Q = fma(r, gq.y, a.Q * keep);
+    if ((rg.ends >> kk) & 1u) {
+        const int j = (int)((rg.spans >> (3 * kk)) & 7u);
+        double *s = ls.scr + (long)(j * NSUM) * ls.ls;
+        s[0] = a.R0; s[ls.ls] = a.R1; s[2 * ls.ls] = a.R2; s[3 * ls.ls] = a.G; s[4 * ls.ls] = a.Q;
+    }
 }
 
-// PASS 1: flexibility sums of the lane's elements, one partial per span in the lane's scratch column
 template <int EPL>
 OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls)
 {
-    int jc = (int)(rg.spans & 7u);
-    double R0 = 0.0, R1 = 0.0, R2 = 0.0, G = 0.0, Q = 0.0;
+    SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) {
-        const int j = (int)((rg.spans >> (3 * kk)) & 7u);
-        if (j != jc) {
-            if (jc != DUMMY) flush_span(ls, jc, R0, R1, R2, G, Q);
-            R0 = R1 = R2 = G = Q = 0.0;
-            jc = j;
-        }
-        const double r = fm::rcp64((double)rg.I[kk]);
-        const double ke = (double)rg.ke[kk];
-        const double t = r * ke;
-        R0 += r;
-        R1 += t;
-        R2 = fma(t, ke, R2);
-        G = fma(r, ls.gc[(long)kk * ls.ls], G);
-        Q = fma(r, ls.qc[(long)kk * ls.ls], Q);
-    }
-    if (jc != DUMMY) flush_span(ls, jc, R0, R1, R2, G, Q);
+    for (int kk = 0; kk < EPL; ++kk) pass1_element<EPL>(rg, ls, kk, a);
 }
 
-// group reduction of the partials: lane l owns the sums p = l, l + 8, ... and adds the eight lanes'
-// partials in the fixed order l, l+1, ... (mod 8) -- deterministic and bank-conflict free
-OPS_HD void lane_reduce(int l, const LaneStore &ls, const GroupStore &gs)
+// Group reduction of the partials and the flexibility coefficients of the span: lane j < NSPAN adds
+// the eight lanes' partials of span j in the fixed order j, j+1, ... (mod 8) -- deterministic and
+// bank-conflict free -- and leaves a, b, c, p, q (without the Le/(6E) factor) in the span's slots.
+OPS_HD void lane_reduce(int l, int m, const LaneStore &ls, const GroupStore &gs)
 {
-    const double *scr0 = ls.scr - l;
+    if (l < m) {
+        const double *scr0 = ls.scr - l + (long)(l * NSUM) * ls.ls;
+        double R[NSUM];
 #pragma unroll
-    for (int i = 0; i < (NSPAN * NSUM + LPB - 1) / LPB; ++i) {
-        const int p = l + LPB * i;
-        if (p < NSPAN * NSUM) {
+        for (int i = 0; i < NSUM; ++i) {
             double s = 0.0;
 #pragma unroll
-            for (int r = 0; r < LPB; ++r) s += scr0[(long)p * ls.ls + ((l + r) & (LPB - 1))];
-            gs.fs.span(p / NSUM + 1, FlexStore::A + p % NSUM) = s;
+            for (int r = 0; r < LPB; ++r) s += scr0[(long)i * ls.ls + ((l + r) & (LPB - 1))];
+            R[i] = s;
         }
+        const double d = gs.fs.span(l + 1, FlexStore::DXI);
+        const double c = (d * d) * fma(6.0, R[2], fma(6.0, R[1], 2.0 * R[0]));
+        const double S = d * fma(2.0, R[1], R[0]);
+        gs.fs.span(l + 1, FlexStore::A) = fma(-6.0, S, fma(6.0, R[0], c));
+        gs.fs.span(l + 1, FlexStore::B) = fma(3.0, S, -c);
+        gs.fs.span(l + 1, FlexStore::C) = c;
+        gs.fs.span(l + 1, FlexStore::P) = R[3] - R[4];
+        gs.fs.span(l + 1, FlexStore::Q) = R[4];
     }
-}
-
-// flexibility coefficients of span j (0-based) from its reduced sums, without the Le/(6E) factor
-OPS_HD void span_flex(const GroupStore &gs, int j, double &a, double &b, double &c, double &p, double &q, double &d)
-{
-    const double R0 = gs.fs.span(j + 1, FlexStore::A), R1 = gs.fs.span(j + 1, FlexStore::B);
-    const double R2 = gs.fs.span(j + 1, FlexStore::C), G = gs.fs.span(j + 1, FlexStore::P);
-    q = gs.fs.span(j + 1, FlexStore::Q);
-    d = gs.fs.span(j + 1, FlexStore::DXI);
-    c = (d * d) * fma(6.0, R2, fma(6.0, R1, 2.0 * R0));
-    const double S = d * fma(2.0, R1, R0);
-    b = fma(3.0, S, -c);
-    a = fma(-6.0, S, fma(6.0, R0, c));
-    p = G - q;
 }
 
 // three-moment system for the support moments (every lane, redundantly); lane 0 publishes the
@@ -248,7 +264,11 @@ OPS_HD int group_solve(const FlexBeam &fb, const GroupStore &gs, int l)
     for (int j = 0; j < NSPAN; ++j) {
         a[j] = b[j] = c[j] = p[j] = q[j] = 0.0;
         dx[j] = 0.0;
-        if (j < m) span_flex(gs, j, a[j], b[j], c[j], p[j], q[j], dx[j]);
+        if (j < m) {
+            a[j] = gs.fs.span(j + 1, FlexStore::A); b[j] = gs.fs.span(j + 1, FlexStore::B);
+            c[j] = gs.fs.span(j + 1, FlexStore::C); p[j] = gs.fs.span(j + 1, FlexStore::P);
+            q[j] = gs.fs.span(j + 1, FlexStore::Q); dx[j] = gs.fs.span(j + 1, FlexStore::DXI);
+        }
     }
     double MS[NSPAN + 1];
     MS[0] = 0.0;
@@ -288,20 +308,27 @@ OPS_HD int group_solve(const FlexBeam &fb, const GroupStore &gs, int l)
     }
     if (l == 0) {
 #pragma unroll
-        for (int j = 0; j <= NSPAN; ++j) {
+        for (int j = 0; j < NSPAN; ++j) {
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-            if (j < NSPAN && j < m) {
+            if (j < m) {
                 const double dM = MS[j + 1] - MS[j];
                 t0 = MS[j];
                 t1 = dM * dx[j];
                 t2 = t1 * fb.invLe;
             }
-            gs.tab[(long)(3 * j) * gs.gs] = t0;
-            gs.tab[(long)(3 * j + 1) * gs.gs] = t1;
-            gs.tab[(long)(3 * j + 2) * gs.gs] = t2;
+            Pair lo, hi;
+            lo.x = t0; lo.y = t1; hi.x = t2; hi.y = 0.0;
+            Pair *row = reinterpret_cast<Pair *>(gs.tab + TAB_ROW * j);
+            row[0] = lo; row[1] = hi;
         }
+        // the DUMMY row (overhang, padding) stays zero: written once per beam by group_table_init
     }
     return bad;
+}
+
+OPS_HD void group_table_init(const GroupStore &gs)
+{
+    for (int i = 0; i < TAB_SLOTS; ++i) gs.tab[i] = 0.0;
 }
 
 // bending moment (three-moment sign: sagging positive) and shear at the node-i end of slot kk
@@ -310,10 +337,11 @@ OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const G
                            double &Mc, double &Qv)
 {
     const int j = (int)((rg.spans >> (3 * kk)) & 7u);
-    const double *t = gs.tab + (long)(3 * j) * gs.gs;
-    const double T0 = t[0], T1 = t[gs.gs], T2 = t[2 * gs.gs];
-    Mc = fma(T1, (double)rg.ke[kk], ls.m0[(long)kk * ls.ls] + T0);
-    Qv = ls.q0[(long)kk * ls.ls] + T2;
+    const Pair *row = reinterpret_cast<const Pair *>(gs.tab + TAB_ROW * j);
+    const Pair lo = row[0], hi = row[1];
+    const Pair mq = ls.mq[(long)kk * ls.ls];
+    Mc = fma(lo.y, (double)rg.ke[kk], mq.x + lo.x);
+    Qv = mq.y + hi.x;
 }
 
 // loss terms d, q and autograd's gradient with M, V constant (element_update_f32, first half), with
@@ -330,7 +358,7 @@ OPS_HD void element_grad(const BeamConsts &k, float I, float c, float h, float &
     const float rgg = fm::rcp_r(gg);
     q = fm::div_r(h, gg, rgg);
     const float qg = fm::div_r(q, gg, rgg);
-    const float is = fm::div_f(1.0f, s);
+    const float is = fm::rcp_f(s);
     const float gb = ((-k.am) * db) * k.E2;
     const float gs_ = ((((-k.as_) * qg) * k.Gf) * k.kf) * (0.5f * is);
     g = (1.0f + gs_) + gb;
@@ -383,11 +411,12 @@ OPS_HD float group_loss(const BeamConsts &k, int n, const LaneStore &ls, int l)
     return (s[0] + k.am * s[1]) + k.as_ * s[2];
 }
 
-// Adam step + clamp on the lane's elements (element_update_f32, second half).  The fast square root
-// needs v >= 2^-101; v is an EMA of g^2, so anything smaller means g vanished on every epoch so far --
+// Adam step + clamp on the lane's elements (element_update_f32, second half) and, fused behind it
+// when PASS1 is set, PASS 1 of the NEXT epoch on the updated inertias.  The fast square root needs
+// v >= 2^-101; v is an EMA of g^2, so anything smaller means g vanished on every epoch so far --
 // tested once per lane and epoch, with the generic operators as the (cold) alternative.
-template <int EPL>
-OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, float neg_step, float bc2_sqrt)
+template <int EPL, bool PASS1>
+OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &ls, float neg_step, float bc2_sqrt)
 {
     bool rare = false;
 #pragma unroll
@@ -399,11 +428,13 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, float neg_step, fl
     }
     if (!rare) {
         const float rbc = fm::rcp_r(bc2_sqrt);
+        SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int kk = 0; kk < EPL; ++kk) {
             const float denom = fm::div_r(fm::sqrt_f(rg.v[kk]), bc2_sqrt, rbc) + k.adam_epsf;
             const float x = rg.I[kk] + fm::div_f(neg_step * rg.m[kk], denom);
             rg.I[kk] = x < k.clampf ? k.clampf : x;
+            if (PASS1) pass1_element<EPL>(rg, ls, kk, a);
         }
     } else {
 #pragma unroll 1
@@ -412,6 +443,7 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, float neg_step, fl
             const float x = rg.I[kk] + (neg_step * rg.m[kk]) / denom;
             rg.I[kk] = x < k.clampf ? k.clampf : x;
         }
+        if (PASS1) lane_pass1<EPL>(rg, ls);
     }
 }
 
@@ -448,12 +480,10 @@ OPS_HD void group_emit_displacements(const BeamConsts &k, const FlexBeam &fb, co
     }
     const int m = fb.m;
     for (int j = 0; j < m; ++j) {
-        double a, b, c, p, q, d;
-        span_flex(gs, j, a, b, c, p, q, d);
-        gs.fs.span(j + 1, FlexStore::A) = fb.kc6 * a;
-        gs.fs.span(j + 1, FlexStore::B) = fb.kc6 * b;
-        gs.fs.span(j + 1, FlexStore::P) = fb.kc6 * p;
-        gs.fs.ms(j) = gs.tab[(long)(3 * j) * gs.gs];
+        gs.fs.span(j + 1, FlexStore::A) *= fb.kc6;
+        gs.fs.span(j + 1, FlexStore::B) *= fb.kc6;
+        gs.fs.span(j + 1, FlexStore::P) *= fb.kc6;
+        gs.fs.ms(j) = gs.tab[TAB_ROW * j];
     }
     gs.fs.ms(m) = fb.Moh;
     const float *stage = reinterpret_cast<const float *>(ls0.scr);

@@ -225,22 +225,22 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
 {
     using namespace ops::lanes;
     const int n = k.n, nn = k.nn;
-    std::vector<double> lane_d((size_t)lane_doubles(EPL) * LPB), grp_d(GROUP_DOUBLES);
+    std::vector<Pair> lane_p((size_t)2 * EPL * LPB);
+    std::vector<double> lane_s((size_t)SCR_SLOTS * LPB), grp_d(GROUP_DOUBLES);
+    std::vector<Pair> tab_p(TAB_SLOTS / 2);
     std::vector<int> grp_i(GROUP_INTS);
     LaneStore ls[LPB];
     for (int l = 0; l < LPB; ++l) {
         ls[l].ls = LPB;
-        ls[l].gc = lane_d.data() + l;
-        ls[l].qc = ls[l].gc + (size_t)EPL * LPB;
-        ls[l].m0 = ls[l].qc + (size_t)EPL * LPB;
-        ls[l].q0 = ls[l].m0 + (size_t)EPL * LPB;
-        ls[l].scr = ls[l].q0 + (size_t)EPL * LPB;
+        ls[l].gq = lane_p.data() + l;
+        ls[l].mq = ls[l].gq + (size_t)EPL * LPB;
+        ls[l].scr = lane_s.data() + l;
     }
     GroupStore gs;
     gs.gs = 1;
+    gs.tab = reinterpret_cast<double *>(tab_p.data());
     gs.fs.sd = grp_d.data(); gs.fs.stride = 1;
-    gs.tab = gs.fs.sd + FlexStore::NUM_DOUBLES;
-    gs.gd = gs.tab + TAB_SLOTS;
+    gs.gd = gs.fs.sd + FlexStore::NUM_DOUBLES;
     gs.fs.si = grp_i.data();
     gs.gi = gs.fs.si + FlexStore::NUM_INTS;
     for (int64_t b = 0; b < B; ++b) {
@@ -257,10 +257,11 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             FlexBeam f0;
             const int rc = flex_setup(k, L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode, fval, gs.fs, f0);
             group_publish(f0, rc, gs);
+            group_table_init(gs);
         }
         int bad = group_fetch(k, L[b], gs, fb);
         for (int l = 0; l < LPB; ++l) {
-            if (!bad) lane_init<EPL>(k, n, fb, gs, ls[l], l, rg[l]);
+            if (!bad) { lane_init<EPL>(k, n, fb, gs, ls[l], l, rg[l]); lane_pass1<EPL>(rg[l], ls[l]); }
             else lane_reset<EPL>(k, rg[l]);
         }
         int t = 0, counter = 0;
@@ -269,8 +270,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
         bool done = (k.max_epochs <= 0) || bad;
         while (!done) {
             neg_step = sched[2 * t]; bc2_sqrt = sched[2 * t + 1];
-            for (int l = 0; l < LPB; ++l) lane_pass1<EPL>(rg[l], ls[l]);
-            for (int l = 0; l < LPB; ++l) lane_reduce(l, ls[l], gs);
+            for (int l = 0; l < LPB; ++l) lane_reduce(l, fb.m, ls[l], gs);
             int rc = 0;
             for (int l = LPB - 1; l >= 0; --l) rc = group_solve(fb, gs, l);
             for (int l = 0; l < LPB; ++l) lane_forces<EPL>(k, n, rg[l], ls[l], gs, l);
@@ -286,7 +286,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
                 if (counter >= k.patience) done = true;
             }
             if (t >= k.max_epochs) done = true;
-            if (!done) for (int l = 0; l < LPB; ++l) lane_adam<EPL>(k, rg[l], neg_step, bc2_sqrt);
+            if (!done) for (int l = 0; l < LPB; ++l) lane_adam<EPL, true>(k, rg[l], ls[l], neg_step, bc2_sqrt);
         }
         const bool fields = (t > 0) && (bad == 0);
         for (int l = 0; l < LPB; ++l)
@@ -294,7 +294,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
         group_emit_displacements(k, fb, ls[0], gs, fields, defl + b * nn, rot + b * nn);
         epochs[b] = t; loss[b] = lossf; status[b] = bad;
         for (int l = 0; l < LPB; ++l) {
-            if (t > 0) lane_adam<EPL>(k, rg[l], neg_step, bc2_sqrt);
+            if (t > 0) lane_adam<EPL, false>(k, rg[l], ls[l], neg_step, bc2_sqrt);
             lane_emit_inertias<EPL>(n, rg[l], l, I_values + b * n);
         }
     }
