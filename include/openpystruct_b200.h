@@ -151,6 +151,41 @@ int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
                          int device, float *elapsed_ms);
 
 /*
+ * Host-buffer SESSION: the same work as ops_beamopt_run_host for callers that generate many batches
+ * (the reference's main() loop over joblib batches, MultiCore:246-262).  The session owns the device
+ * buffers, a stream and PINNED host buffers for one device and up to max_beams beams per run, so a
+ * run costs one H2D copy of the inputs, one launch and one D2H copy of the record arrays -- no
+ * allocation, no page faults on fresh host pages.
+ *
+ *   ops_beamopt_session_create   allocates everything (returns 0 / OPS_E_* / cudaError_t)
+ *   ops_beamopt_session_arrays   the pinned host arrays (layouts of ops_beamopt_launch, max_beams rows):
+ *                                the caller fills the four input arrays in place before a run and
+ *                                reads the eight output arrays after it (valid until the next run)
+ *   ops_beamopt_session_run      H2D, launch, D2H, synchronise for the first B beams; elapsed_ms
+ *                                (optional) = device time of the launch alone
+ *   ops_beamopt_session_destroy  frees everything
+ */
+typedef struct OpsBeamOptSession OpsBeamOptSession;
+
+typedef struct OpsBeamOptHostArrays {
+    uint8_t *fixed_uy;
+    int32_t *force_nodes;
+    double *force_vals;
+    double *L;
+    float *I_values;
+    double *deflections, *rotations;
+    float *shear, *moment;
+    int32_t *epochs;
+    float *loss;
+    int32_t *status;
+} OpsBeamOptHostArrays;
+
+int ops_beamopt_session_create(const OpsBeamOptParams *p, int64_t max_beams, int device, OpsBeamOptSession **out);
+int ops_beamopt_session_arrays(OpsBeamOptSession *s, OpsBeamOptHostArrays *arrays);
+int ops_beamopt_session_run(OpsBeamOptSession *s, int64_t B, float *elapsed_ms);
+void ops_beamopt_session_destroy(OpsBeamOptSession *s);
+
+/*
  * Diagnostic for the roofline denominator (no reference counterpart): runs `chains` independent
  * DFMA chains of length `iters` per thread on a full grid of the current device and reports the
  * sustained FP64 rate in TFLOP/s (FMA = 2 flop), timed with CUDA events on `cuda_stream`.

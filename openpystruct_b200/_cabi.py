@@ -16,6 +16,8 @@ EXPORTS = (
     "ops_beamopt_version", "ops_device_count", "ops_set_device", "ops_beamopt_fill_schedule",
     "ops_beamopt_workspace_bytes", "ops_beamopt_launch", "ops_beamsolve_launch", "ops_beamopt_run_host",
     "ops_fp64_peak_probe", "ops_fastmath_selftest",
+    "ops_beamopt_session_create", "ops_beamopt_session_arrays", "ops_beamopt_session_run",
+    "ops_beamopt_session_destroy",
 )
 
 
@@ -31,6 +33,11 @@ class OpsBeamOptParams(C.Structure):
         ("bending_eps", C.c_double), ("clamp_min", C.c_double), ("beta1", C.c_double),
         ("beta2", C.c_double), ("adam_eps", C.c_double),
     ]
+
+
+class OpsBeamOptHostArrays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("fixed_uy", "force_nodes", "force_vals", "L", "I_values", "deflections",
+                                          "rotations", "shear", "moment", "epochs", "loss", "status")]
 
 
 class CudaLibraryError(RuntimeError):
@@ -49,11 +56,12 @@ def lib():
     """The loaded CUDA library; raises CudaLibraryError when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("OPS_B200_LIB", LIB_PATH)      # A/B builds of the same ABI (profiling)
+        if not os.path.exists(path):
             raise CudaLibraryError(
-                f"{LIB_PATH} is missing: build it with `python -m openpystruct_b200.build` "
+                f"{path} is missing: build it with `python -m openpystruct_b200.build` "
                 "(there is no CPU fallback for this path)")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         L.ops_beamopt_version.restype = C.c_char_p
         L.ops_device_count.restype = C.c_int
         L.ops_set_device.argtypes = [C.c_int]
@@ -69,6 +77,12 @@ def lib():
         L.ops_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p]
         L.ops_fastmath_selftest.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                             C.POINTER(C.c_double), C.c_void_p]
+        L.ops_beamopt_session_create.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64, C.c_int,
+                                                 C.POINTER(C.c_void_p)]
+        L.ops_beamopt_session_arrays.argtypes = [C.c_void_p, C.POINTER(OpsBeamOptHostArrays)]
+        L.ops_beamopt_session_run.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float)]
+        L.ops_beamopt_session_destroy.argtypes = [C.c_void_p]
+        L.ops_beamopt_session_destroy.restype = None
         _lib = L
     return _lib
 
@@ -133,3 +147,80 @@ def fastmath_selftest(samples: int = 1 << 26, stream: int = 0) -> dict:
     check(lib().ops_fastmath_selftest(samples, mism, C.byref(ran), C.byref(worst), stream), "ops_fastmath_selftest")
     return {"div": int(mism[0]), "sqrt": int(mism[1]), "rcp": int(mism[2]), "samples": int(ran.value),
             "rcp64_max_rel_err": float(worst.value)}
+
+
+class Session:
+    """ops_beamopt_session_*: persistent device buffers + pinned host arrays for up to ``max_beams``
+    beams per run.  ``inputs`` / ``outputs`` are numpy VIEWS of the pinned arrays: fill the inputs in
+    place (or use ``load``), call ``run(B)``, read the first B rows of the outputs (valid until the
+    next run)."""
+
+    def __init__(self, p: BeamOptParams, max_beams: int, device: int = 0):
+        self.p, self.max_beams, self.device = p, int(max_beams), device
+        self._cp = to_c_params(p)
+        self._h = C.c_void_p()
+        check(lib().ops_beamopt_session_create(C.byref(self._cp), self.max_beams, device, C.byref(self._h)),
+              "ops_beamopt_session_create")
+        arr = OpsBeamOptHostArrays()
+        check(lib().ops_beamopt_session_arrays(self._h, C.byref(arr)), "ops_beamopt_session_arrays")
+        B, nn, Cc, F = self.max_beams, p.num_nodes, p.num_cases, p.max_forces
+        n = nn - 1
+
+        def view(ptr, shape, dtype):
+            count = int(np.prod(shape))
+            if count == 0:
+                return np.zeros(shape, dtype)
+            ctype = np.ctypeslib.as_ctypes_type(dtype)
+            buf = (ctype * count).from_address(ptr)
+            return np.ctypeslib.as_array(buf).reshape(shape)
+
+        self.inputs = {
+            "fixed_uy": view(arr.fixed_uy, (B, nn), np.uint8),
+            "force_nodes": view(arr.force_nodes, (B, Cc, F), np.int32),
+            "force_vals": view(arr.force_vals, (B, Cc, F), np.float64),
+            "L": view(arr.L, (B,), np.float64),
+        }
+        self.outputs = {
+            "I": view(arr.I_values, (B, n), np.float32),
+            "defl": view(arr.deflections, (B, Cc, nn), np.float64),
+            "rot": view(arr.rotations, (B, Cc, nn), np.float64),
+            "shear": view(arr.shear, (B, Cc, n), np.float32),
+            "moment": view(arr.moment, (B, Cc, n), np.float32),
+            "epochs": view(arr.epochs, (B,), np.int32),
+            "loss": view(arr.loss, (B,), np.float32),
+            "status": view(arr.status, (B,), np.int32),
+        }
+        self.kernel_ms = 0.0
+
+    def load(self, fixed_uy, force_nodes, force_vals, L) -> int:
+        B = len(L)
+        if B > self.max_beams:
+            raise ValueError("batch larger than the session")
+        self.inputs["fixed_uy"][:B] = fixed_uy
+        self.inputs["force_nodes"][:B] = np.asarray(force_nodes).reshape(B, self.p.num_cases, self.p.max_forces)
+        self.inputs["force_vals"][:B] = np.asarray(force_vals).reshape(B, self.p.num_cases, self.p.max_forces)
+        self.inputs["L"][:B] = L
+        return B
+
+    def run(self, B: int) -> dict:
+        ms = C.c_float(0.0)
+        check(lib().ops_beamopt_session_run(self._h, int(B), C.byref(ms)), "ops_beamopt_session_run")
+        self.kernel_ms = float(ms.value)
+        return {k: v[:B] for k, v in self.outputs.items()}
+
+    def close(self):
+        if self._h:
+            lib().ops_beamopt_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

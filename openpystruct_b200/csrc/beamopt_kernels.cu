@@ -784,4 +784,123 @@ done:
     return rc;
 }
 
+struct OpsBeamOptSession {
+    OpsBeamOptParams p;
+    int64_t max_beams;
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    unsigned char *dbuf, *hbuf;          // one device and one pinned host allocation, same offsets
+    size_t in_bytes, out_bytes, ws_bytes;
+    size_t o_fixed, o_fn, o_fv, o_L, o_I, o_defl, o_rot, o_sh, o_mo, o_ep, o_loss, o_st, o_sched, o_ws;
+};
+
+int ops_beamopt_session_create(const OpsBeamOptParams *p, int64_t max_beams, int device, OpsBeamOptSession **out)
+{
+    BeamConsts k;
+    int rc = make_consts(p, &k);
+    if (rc) return rc;
+    if (!out || max_beams <= 0) return OPS_E_BADARG;
+    OpsBeamOptSession *s = (OpsBeamOptSession *)calloc(1, sizeof *s);
+    if (!s) return OPS_E_BADARG;
+    s->p = *p; s->max_beams = max_beams; s->device = device;
+    const size_t B = (size_t)max_beams, nn = k.nn, n = k.n, C = 1, F = (size_t)p->max_forces;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    // inputs first (one contiguous H2D range), then outputs (one contiguous D2H range), then device-only
+    s->o_fixed = take(B * nn); s->o_fn = take(B * C * F * 4); s->o_fv = take(B * C * F * 8); s->o_L = take(B * 8);
+    s->in_bytes = off;
+    s->o_I = take(B * n * 4); s->o_defl = take(B * C * nn * 8); s->o_rot = take(B * C * nn * 8);
+    s->o_sh = take(B * C * n * 4); s->o_mo = take(B * C * n * 4);
+    s->o_ep = take(B * 4); s->o_loss = take(B * 4); s->o_st = take(B * 4);
+    s->out_bytes = off - s->in_bytes;
+    const size_t host_bytes = off;
+    s->o_sched = take((size_t)(p->max_epochs > 0 ? p->max_epochs : 1) * 8);
+    float *sched_h = nullptr;
+    OPS_CUDA(cudaSetDevice(device));
+    s->ws_bytes = ops_beamopt_workspace_bytes(p, max_beams);
+    if (s->ws_bytes == 0) { rc = OPS_E_BADARG; goto done; }
+    s->o_ws = take(s->ws_bytes);
+    OPS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    OPS_CUDA(cudaEventCreate(&s->ev0));
+    OPS_CUDA(cudaEventCreate(&s->ev1));
+    OPS_CUDA(cudaMalloc((void **)&s->dbuf, off));
+    OPS_CUDA(cudaHostAlloc((void **)&s->hbuf, host_bytes, cudaHostAllocDefault));
+    memset(s->hbuf, 0, host_bytes);
+    sched_h = (float *)malloc((size_t)(p->max_epochs > 0 ? p->max_epochs : 1) * 8);
+    if (!sched_h) { rc = OPS_E_BADARG; goto done; }
+    ops_beamopt_fill_schedule(p, sched_h);
+    OPS_CUDA(cudaMemcpyAsync(s->dbuf + s->o_sched, sched_h, (size_t)(p->max_epochs > 0 ? p->max_epochs : 1) * 8,
+                             cudaMemcpyHostToDevice, s->stream));
+    OPS_CUDA(cudaStreamSynchronize(s->stream));
+done:
+    free(sched_h);
+    if (rc) { ops_beamopt_session_destroy(s); if (rc > 0) cudaGetLastError(); return rc; }
+    *out = s;
+    return 0;
+}
+
+int ops_beamopt_session_arrays(OpsBeamOptSession *s, OpsBeamOptHostArrays *a)
+{
+    if (!s || !a) return OPS_E_BADARG;
+    unsigned char *h = s->hbuf;
+    a->fixed_uy = h + s->o_fixed; a->force_nodes = (int32_t *)(h + s->o_fn); a->force_vals = (double *)(h + s->o_fv);
+    a->L = (double *)(h + s->o_L); a->I_values = (float *)(h + s->o_I); a->deflections = (double *)(h + s->o_defl);
+    a->rotations = (double *)(h + s->o_rot); a->shear = (float *)(h + s->o_sh); a->moment = (float *)(h + s->o_mo);
+    a->epochs = (int32_t *)(h + s->o_ep); a->loss = (float *)(h + s->o_loss); a->status = (int32_t *)(h + s->o_st);
+    return 0;
+}
+
+int ops_beamopt_session_run(OpsBeamOptSession *s, int64_t B, float *elapsed_ms)
+{
+    if (!s || B < 0 || B > s->max_beams) return OPS_E_BADARG;
+    if (B == 0) return 0;
+    int rc = 0;
+    const size_t nn = (size_t)s->p.num_nodes, n = nn - 1, F = (size_t)s->p.max_forces, b = (size_t)B;
+    unsigned char *d = s->dbuf, *h = s->hbuf;
+    auto h2d = [&](size_t o, size_t bytes) { return cudaMemcpyAsync(d + o, h + o, bytes, cudaMemcpyHostToDevice, s->stream); };
+    auto d2h = [&](size_t o, size_t bytes) { return cudaMemcpyAsync(h + o, d + o, bytes, cudaMemcpyDeviceToHost, s->stream); };
+    OPS_CUDA(cudaSetDevice(s->device));
+    if (B == s->max_beams) {
+        OPS_CUDA(h2d(0, s->in_bytes));
+    } else {
+        OPS_CUDA(h2d(s->o_fixed, b * nn));
+        if (F > 0) { OPS_CUDA(h2d(s->o_fn, b * F * 4)); OPS_CUDA(h2d(s->o_fv, b * F * 8)); }
+        OPS_CUDA(h2d(s->o_L, b * 8));
+    }
+    OPS_CUDA(cudaEventRecord(s->ev0, s->stream));
+    rc = ops_beamopt_launch(&s->p, B, d + s->o_fixed, (const int32_t *)(d + s->o_fn), (const double *)(d + s->o_fv),
+                            (const double *)(d + s->o_L), (const float *)(d + s->o_sched), (float *)(d + s->o_I),
+                            (double *)(d + s->o_defl), (double *)(d + s->o_rot), (float *)(d + s->o_sh),
+                            (float *)(d + s->o_mo), (int32_t *)(d + s->o_ep), (float *)(d + s->o_loss),
+                            (int32_t *)(d + s->o_st), d + s->o_ws, s->ws_bytes, s->stream);
+    if (rc) goto done;
+    OPS_CUDA(cudaEventRecord(s->ev1, s->stream));
+    if (B == s->max_beams) {
+        OPS_CUDA(d2h(s->in_bytes, s->out_bytes));
+    } else {
+        OPS_CUDA(d2h(s->o_I, b * n * 4)); OPS_CUDA(d2h(s->o_defl, b * nn * 8)); OPS_CUDA(d2h(s->o_rot, b * nn * 8));
+        OPS_CUDA(d2h(s->o_sh, b * n * 4)); OPS_CUDA(d2h(s->o_mo, b * n * 4));
+        OPS_CUDA(d2h(s->o_ep, b * 4)); OPS_CUDA(d2h(s->o_loss, b * 4)); OPS_CUDA(d2h(s->o_st, b * 4));
+    }
+    OPS_CUDA(cudaStreamSynchronize(s->stream));
+    if (elapsed_ms) OPS_CUDA(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+done:
+    if (rc > 0) cudaGetLastError();
+    return rc;
+}
+
+void ops_beamopt_session_destroy(OpsBeamOptSession *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->dbuf) cudaFree(s->dbuf);
+    if (s->hbuf) cudaFreeHost(s->hbuf);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    free(s);
+}
+
 }  // extern "C"

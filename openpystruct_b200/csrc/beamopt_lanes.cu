@@ -20,7 +20,10 @@ namespace ops {
 
 using namespace lanes;
 
-constexpr int LANES_MAX_THREADS = 320;
+#ifndef OPS_LANES_MAXT
+#define OPS_LANES_MAXT 320
+#endif
+constexpr int LANES_MAX_THREADS = OPS_LANES_MAXT;
 
 template <int EPL, int NFIX>
 __global__ void __launch_bounds__(LANES_MAX_THREADS, 1)

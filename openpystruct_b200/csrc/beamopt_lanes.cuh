@@ -40,8 +40,8 @@ constexpr int DUMMY = NSPAN;                    // span id of overhang elements 
 constexpr int NSUM = 5;                         // R0, R1, R2, G, Q
 constexpr int SCR_STAGE = NSPAN * NSUM;         // 3 slots after the partial sums: {row sum, tail} of sum I, d, q
 constexpr int SCR_SLOTS = SCR_STAGE + 3;
-constexpr int TAB_ROW = 4;                      // per span: MS_l, (MS_r - MS_l) d, (MS_r - MS_l) d / Le, pad
-constexpr int TAB_SLOTS = (NSPAN + 1) * TAB_ROW + 2;   // contiguous per group; +2 keeps four groups on distinct banks
+constexpr int TAB_T2 = 2 * (NSPAN + 1);         // span table: Pair {MS_l, (MS_r - MS_l) d} [6], then (MS_r - MS_l) d / Le [6]
+constexpr int TAB_SLOTS = 3 * (NSPAN + 1) + 2;  // contiguous per group; +2 keeps the four groups of a warp on distinct banks
 constexpr int GX_DOUBLES = 2;                   // Moh, Qoh
 constexpr int GX_INTS = 4;                      // m, last, nloads, setup status
 constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + GX_DOUBLES;   // strided [slot][group] columns (+ TAB_SLOTS contiguous)
@@ -201,10 +201,9 @@ struct SpanSums {
 };
 
 template <int EPL>
-OPS_HD void pass1_element(const LaneRegs<EPL> &rg, const LaneStore &ls, int kk, SpanSums &a)
+OPS_HD void pass1_accumulate(const LaneRegs<EPL> &rg, const LaneStore &ls, int kk, double r, SpanSums &a)
 {
     const double keep = ((rg.starts >> kk) & 1u) ? 0.0 : 1.0;
-    const double r = fm::rcp64((double)rg.I[kk]);
     const double ke = (double)rg.ke[kk];
     const Pair gq = ls.gq[(long)kk * ls.ls];
     const double t = r * ke;
@@ -225,25 +224,27 @@ OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls)
 {
     SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) pass1_element<EPL>(rg, ls, kk, a);
+    for (int kk = 0; kk < EPL; ++kk) pass1_accumulate<EPL>(rg, ls, kk, fm::rcp64((double)rg.I[kk]), a);
 }
 
 // Group reduction of the partials and the flexibility coefficients of the span: lane j < NSPAN adds
 // the eight lanes' partials of span j in the fixed order j, j+1, ... (mod 8) -- deterministic and
-// bank-conflict free -- and leaves a, b, c, p, q (without the Le/(6E) factor) in the span's slots.
+// bank-conflict free -- and leaves a, b, c, p, q (without the Le/(6E) factor) in the span's slots
+// (zeros for the unused spans j >= m, whose partials are never written).
 OPS_HD void lane_reduce(int l, int m, const LaneStore &ls, const GroupStore &gs)
 {
-    if (l < m) {
+    if (l < NSPAN) {
         const double *scr0 = ls.scr - l + (long)(l * NSUM) * ls.ls;
         double R[NSUM];
 #pragma unroll
         for (int i = 0; i < NSUM; ++i) {
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < LPB; ++r) s += scr0[(long)i * ls.ls + ((l + r) & (LPB - 1))];
-            R[i] = s;
+            double s0 = scr0[(long)i * ls.ls + ((l + 0) & 7)] + scr0[(long)i * ls.ls + ((l + 1) & 7)];
+            double s1 = scr0[(long)i * ls.ls + ((l + 2) & 7)] + scr0[(long)i * ls.ls + ((l + 3) & 7)];
+            double s2 = scr0[(long)i * ls.ls + ((l + 4) & 7)] + scr0[(long)i * ls.ls + ((l + 5) & 7)];
+            double s3 = scr0[(long)i * ls.ls + ((l + 6) & 7)] + scr0[(long)i * ls.ls + ((l + 7) & 7)];
+            R[i] = (s0 + s1) + (s2 + s3);
         }
-        const double d = gs.fs.span(l + 1, FlexStore::DXI);
+        const double d = (l < m) ? gs.fs.span(l + 1, FlexStore::DXI) : 0.0;
         const double c = (d * d) * fma(6.0, R[2], fma(6.0, R[1], 2.0 * R[0]));
         const double S = d * fma(2.0, R[1], R[0]);
         gs.fs.span(l + 1, FlexStore::A) = fma(-6.0, S, fma(6.0, R[0], c));
@@ -254,76 +255,66 @@ OPS_HD void lane_reduce(int l, int m, const LaneStore &ls, const GroupStore &gs)
     }
 }
 
-// three-moment system for the support moments (every lane, redundantly); lane 0 publishes the
-// per-span table PASS 2 reads.  Returns 1 when a pivot is not positive.
+// Three-moment system for the support moments (every lane, redundantly): unknowns MS[1..m-1],
+// MS[0] = 0 (pinned end), MS[m] = overhang moment, Thomas elimination written without data-dependent
+// control flow (rows kk >= m are computed on zeros and discarded by a select; every array index is a
+// compile-time constant, so the working set stays in registers).  Lane 0 publishes the per-span table
+// PASS 2 reads.  Returns 1 when a pivot of a real row is not positive.
 OPS_HD int group_solve(const FlexBeam &fb, const GroupStore &gs, int l)
 {
     const int m = fb.m;
-    double a[NSPAN], b[NSPAN], c[NSPAN], p[NSPAN], q[NSPAN], dx[NSPAN];
+    double a[NSPAN], b[NSPAN], c[NSPAN], p[NSPAN], q[NSPAN];
 #pragma unroll
     for (int j = 0; j < NSPAN; ++j) {
-        a[j] = b[j] = c[j] = p[j] = q[j] = 0.0;
-        dx[j] = 0.0;
-        if (j < m) {
-            a[j] = gs.fs.span(j + 1, FlexStore::A); b[j] = gs.fs.span(j + 1, FlexStore::B);
-            c[j] = gs.fs.span(j + 1, FlexStore::C); p[j] = gs.fs.span(j + 1, FlexStore::P);
-            q[j] = gs.fs.span(j + 1, FlexStore::Q); dx[j] = gs.fs.span(j + 1, FlexStore::DXI);
-        }
+        a[j] = gs.fs.span(j + 1, FlexStore::A); b[j] = gs.fs.span(j + 1, FlexStore::B);
+        c[j] = gs.fs.span(j + 1, FlexStore::C); p[j] = gs.fs.span(j + 1, FlexStore::P);
+        q[j] = gs.fs.span(j + 1, FlexStore::Q);
     }
     double MS[NSPAN + 1];
     MS[0] = 0.0;
 #pragma unroll
     for (int j = 1; j <= NSPAN; ++j) MS[j] = (j == m) ? fb.Moh : 0.0;
-    int bad = 0;
+    bool bad = false;
     double inv[NSPAN], rr[NSPAN];
     double ip = 0.0, rp = 0.0;
 #pragma unroll
     for (int kk = 1; kk < NSPAN; ++kk) {
-        inv[kk] = 0.0; rr[kk] = 0.0;
-        if (kk < m) {
-            double dd = c[kk - 1] + a[kk];
-            double r_ = -(q[kk - 1] + p[kk]);
-            if (kk == m - 1) r_ = fma(-b[kk], fb.Moh, r_);
-            if (kk > 1) {
-                const double bk = b[kk - 1];
-                const double w = bk * ip;
-                dd = fma(-w, bk, dd);
-                r_ = fma(-w, rp, r_);
-            }
-            if (!(dd > 0.0)) bad = 1;
-            ip = fm::rcp64(dd);
-            rp = r_;
-            inv[kk] = ip; rr[kk] = r_;
+        double dd = c[kk - 1] + a[kk];
+        double r_ = -(q[kk - 1] + p[kk]);
+        if (kk > 1) {
+            const double bk = b[kk - 1];
+            const double w = bk * ip;
+            dd = fma(-w, bk, dd);
+            r_ = fma(-w, rp, r_);
         }
+        const bool live = kk < m;
+        bad = bad || (live && !(dd > 0.0));
+        dd = live ? dd : 1.0;
+        ip = fm::rcp64(dd);
+        rp = r_;
+        inv[kk] = ip; rr[kk] = r_;
     }
-    double mnext = fb.Moh;
+    // back substitution; the known end moment MS[m] enters through the same b[kk] MS[kk + 1] term
 #pragma unroll
     for (int kk = NSPAN - 1; kk >= 1; --kk) {
-        if (kk < m) {
-            double r_ = rr[kk];
-            if (kk < m - 1) r_ = fma(-b[kk], mnext, r_);
-            mnext = r_ * inv[kk];
-            MS[kk] = mnext;
-        }
+        const double x = fma(-b[kk], MS[kk + 1], rr[kk]) * inv[kk];
+        MS[kk] = (kk < m) ? x : MS[kk];
     }
     if (l == 0) {
 #pragma unroll
         for (int j = 0; j < NSPAN; ++j) {
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-            if (j < m) {
-                const double dM = MS[j + 1] - MS[j];
-                t0 = MS[j];
-                t1 = dM * dx[j];
-                t2 = t1 * fb.invLe;
-            }
-            Pair lo, hi;
-            lo.x = t0; lo.y = t1; hi.x = t2; hi.y = 0.0;
-            Pair *row = reinterpret_cast<Pair *>(gs.tab + TAB_ROW * j);
-            row[0] = lo; row[1] = hi;
+            const double dxj = gs.fs.span(j + 1, FlexStore::DXI);
+            const bool live = j < m;
+            const double dM = MS[j + 1] - MS[j];
+            const double t1 = live ? dM * dxj : 0.0;
+            Pair lo;
+            lo.x = live ? MS[j] : 0.0; lo.y = t1;
+            reinterpret_cast<Pair *>(gs.tab)[j] = lo;
+            gs.tab[TAB_T2 + j] = t1 * fb.invLe;
         }
         // the DUMMY row (overhang, padding) stays zero: written once per beam by group_table_init
     }
-    return bad;
+    return bad ? 1 : 0;
 }
 
 OPS_HD void group_table_init(const GroupStore &gs)
@@ -337,34 +328,26 @@ OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const G
                            double &Mc, double &Qv)
 {
     const int j = (int)((rg.spans >> (3 * kk)) & 7u);
-    const Pair *row = reinterpret_cast<const Pair *>(gs.tab + TAB_ROW * j);
-    const Pair lo = row[0], hi = row[1];
+    const Pair lo = reinterpret_cast<const Pair *>(gs.tab)[j];
+    const double t2 = gs.tab[TAB_T2 + j];
     const Pair mq = ls.mq[(long)kk * ls.ls];
     Mc = fma(lo.y, (double)rg.ke[kk], mq.x + lo.x);
-    Qv = mq.y + hi.x;
+    Qv = mq.y + t2;
 }
 
-// loss terms d, q and autograd's gradient with M, V constant (element_update_f32, first half), with
-// the branch-free division / square-root sequences.  Ranges: I in [clamp_min, 1e20) (the clamp,
+// Elements are processed in batches of NB slots, STAGE BY STAGE across the batch: the stages of one
+// element are a ~150-cycle dependent chain (MUFU -> Newton -> quotient -> ...), and written element
+// by element ptxas leaves the chains serial at this register budget; stage-major order puts NB
+// independent instructions between dependent ones.
+#ifndef OPS_LANES_NB
+#define OPS_LANES_NB 5
+#endif
+constexpr int NB = OPS_LANES_NB;
+
+// PASS 2: end forces, loss terms d, q and autograd's gradient with M, V constant (element_update_f32,
+// first half; the gradient is kept in rg.g), torch.sum partials of sum I, sum d, sum q.
+// fp32 ranges for the branch-free division / square root: I in [clamp_min, 1e20) (the clamp,
 // SingleCore:208), c = M^2 and h = V^2 zero or >= 2^-100.
-OPS_HD void element_grad(const BeamConsts &k, float I, float c, float h, float &d, float &q, float &g)
-{
-    const float b = k.E2 * I + k.epsf;
-    const float rb = fm::rcp_r(b);
-    d = fm::div_r(c, b, rb);
-    const float db = fm::div_r(d, b, rb);
-    const float s = fm::sqrt_f(I);
-    const float gg = k.Gf * (k.kf * s);
-    const float rgg = fm::rcp_r(gg);
-    q = fm::div_r(h, gg, rgg);
-    const float qg = fm::div_r(q, gg, rgg);
-    const float is = fm::rcp_f(s);
-    const float gb = ((-k.am) * db) * k.E2;
-    const float gs_ = ((((-k.as_) * qg) * k.Gf) * k.kf) * (0.5f * is);
-    g = (1.0f + gs_) + gb;
-}
-
-// PASS 2: end forces, loss terms, gradient (kept in rg.g), torch.sum partials of sum I, sum d, sum q
 template <int EPL>
 OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, int l)
 {
@@ -372,19 +355,66 @@ OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const Lan
     float aI[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ad[4] = {0.0f, 0.0f, 0.0f, 0.0f}, aq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float tI = 0.0f, td = 0.0f, tq = 0.0f;
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) {
-        double Mc, Qv;
-        element_forces<EPL>(rg, ls, gs, kk, Mc, Qv);
-        const float Mf = (float)Mc, Vf = (float)Qv;
-        float d, q;
-        element_grad(k, rg.I[kk], Mf * Mf, Vf * Vf, d, q, rg.g[kk]);
-        if (kk < sh.blk) {
-            aI[kk & 3] += rg.I[kk]; ad[kk & 3] += d; aq[kk & 3] += q;
-        } else if (kk < sh.vec) {
-            aI[0] += rg.I[kk]; ad[0] += d; aq[0] += q;
-        } else if (kk == sh.vec && l < sh.ntail) {
-            tI = rg.I[kk]; td = d; tq = q;
-        }
+    for (int k0 = 0; k0 < EPL; k0 += NB) {
+        double Mc[NB], Qv[NB];
+        float c[NB], h[NB], b[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (k0 + i < EPL) element_forces<EPL>(rg, ls, gs, k0 + i, Mc[i], Qv[i]);
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (k0 + i < EPL) {
+                const float I = rg.I[k0 + i];
+                const float Mf = (float)Mc[i], Vf = (float)Qv[i];
+                c[i] = Mf * Mf;
+                h[i] = Vf * Vf;
+                b[i] = k.E2 * I + k.epsf;
+                y[i] = fm::rsq_a(I);
+                rb[i] = fm::rcp_a(b[i]);
+            }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (k0 + i < EPL) {
+                rb[i] = fm::rcp_n(b[i], rb[i]);
+                s[i] = fm::sqrt_n(rg.I[k0 + i], y[i]);
+                gg[i] = k.Gf * (k.kf * s[i]);
+                rgg[i] = fm::rcp_a(gg[i]);
+                rs[i] = fm::rcp_a(s[i]);
+            }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (k0 + i < EPL) {
+                d[i] = fm::div_r(c[i], b[i], rb[i]);
+                rgg[i] = fm::rcp_n(gg[i], rgg[i]);
+                rs[i] = fm::rcp_n(s[i], rs[i]);
+            }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (k0 + i < EPL) {
+                db[i] = fm::div_r(d[i], b[i], rb[i]);
+                q[i] = fm::div_r(h[i], gg[i], rgg[i]);
+                rs[i] = fm::rcp_fin(s[i], rs[i]);                    // 1 / sqrt(I)
+            }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (k0 + i < EPL) {
+                qg[i] = fm::div_r(q[i], gg[i], rgg[i]);
+                db[i] = ((-k.am) * db[i]) * k.E2;                    // bending branch of the gradient
+            }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (k0 + i < EPL) {
+                const int kk = k0 + i;
+                const float gs_ = ((((-k.as_) * qg[i]) * k.Gf) * k.kf) * (0.5f * rs[i]);
+                rg.g[kk] = (1.0f + gs_) + db[i];
+                if (kk < sh.blk) {
+                    aI[kk & 3] += rg.I[kk]; ad[kk & 3] += d[i]; aq[kk & 3] += q[i];
+                } else if (kk < sh.vec) {
+                    aI[0] += rg.I[kk]; ad[0] += d[i]; aq[0] += q[i];
+                } else if (kk == sh.vec && l < sh.ntail) {
+                    tI = rg.I[kk]; td = d[i]; tq = q[i];
+                }
+            }
     }
     float *st = reinterpret_cast<float *>(ls.scr + (long)SCR_STAGE * ls.ls);
     const long fs_ = 2 * ls.ls;                 // float stride between slots
@@ -412,9 +442,10 @@ OPS_HD float group_loss(const BeamConsts &k, int n, const LaneStore &ls, int l)
 }
 
 // Adam step + clamp on the lane's elements (element_update_f32, second half) and, fused behind it
-// when PASS1 is set, PASS 1 of the NEXT epoch on the updated inertias.  The fast square root needs
-// v >= 2^-101; v is an EMA of g^2, so anything smaller means g vanished on every epoch so far --
-// tested once per lane and epoch, with the generic operators as the (cold) alternative.
+// when PASS1 is set, PASS 1 of the NEXT epoch on the updated inertias (stage-major batches as above).
+// The fast square root needs v >= 2^-101; v is an EMA of g^2, so anything smaller means g vanished on
+// every epoch so far -- tested once per lane and epoch, with the generic operators as the (cold)
+// alternative.
 template <int EPL, bool PASS1>
 OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &ls, float neg_step, float bc2_sqrt)
 {
@@ -430,14 +461,39 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &l
         const float rbc = fm::rcp_r(bc2_sqrt);
         SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int kk = 0; kk < EPL; ++kk) {
-            const float denom = fm::div_r(fm::sqrt_f(rg.v[kk]), bc2_sqrt, rbc) + k.adam_epsf;
-            const float x = rg.I[kk] + fm::div_f(neg_step * rg.m[kk], denom);
-            rg.I[kk] = x < k.clampf ? k.clampf : x;
-            if (PASS1) pass1_element<EPL>(rg, ls, kk, a);
+        for (int k0 = 0; k0 < EPL; k0 += NB) {
+            float y[NB], den[NB], rd[NB];
+            double Id[NB], r[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+                if (k0 + i < EPL) y[i] = fm::rsq_a(rg.v[k0 + i]);
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+                if (k0 + i < EPL) {
+                    den[i] = fm::div_r(fm::sqrt_n(rg.v[k0 + i], y[i]), bc2_sqrt, rbc) + k.adam_epsf;
+                    rd[i] = fm::rcp_a(den[i]);
+                }
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+                if (k0 + i < EPL) {
+                    const float x = rg.I[k0 + i] + fm::div_r(neg_step * rg.m[k0 + i], den[i], fm::rcp_n(den[i], rd[i]));
+                    rg.I[k0 + i] = x < k.clampf ? k.clampf : x;
+                    if (PASS1) {
+                        Id[i] = (double)rg.I[k0 + i];
+                        r[i] = fm::rcp64_a(Id[i]);
+                    }
+                }
+            if (PASS1) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (k0 + i < EPL) r[i] = fm::rcp64_n(Id[i], r[i]);
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (k0 + i < EPL) pass1_accumulate<EPL>(rg, ls, k0 + i, r[i], a);
+            }
         }
     } else {
-#pragma unroll 1
+#pragma unroll                                  // (static indices: a rolled loop would push the state arrays to local memory)
         for (int kk = 0; kk < EPL; ++kk) {
             const float denom = sqrtf(rg.v[kk]) / bc2_sqrt + k.adam_epsf;
             const float x = rg.I[kk] + (neg_step * rg.m[kk]) / denom;
@@ -483,7 +539,7 @@ OPS_HD void group_emit_displacements(const BeamConsts &k, const FlexBeam &fb, co
         gs.fs.span(j + 1, FlexStore::A) *= fb.kc6;
         gs.fs.span(j + 1, FlexStore::B) *= fb.kc6;
         gs.fs.span(j + 1, FlexStore::P) *= fb.kc6;
-        gs.fs.ms(j) = gs.tab[TAB_ROW * j];
+        gs.fs.ms(j) = gs.tab[2 * j];
     }
     gs.fs.ms(m) = fb.Moh;
     const float *stage = reinterpret_cast<const float *>(ls0.scr);

@@ -289,3 +289,19 @@ def test_fine_discretisation_1000_elements():
     g = gpu_solve(p, fixed, fn[:, 0], fv[:, 0], L, I)
     for k in ("defl", "rot", "shear", "moment"):
         assert rel_err(g[k], o80[k]).max() < 1e-9, k
+
+
+def test_session_matches_the_device_pointer_entry():
+    """ops_beamopt_session_*: pinned host arrays in, pinned host arrays out, same bytes as ops_beamopt_launch;
+    partial batches and reuse of one session."""
+    p = BeamOptParams.for_script("MC").replace(max_e=80)
+    cases = seeded_cases(p, 700, seed=106)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    want = gpu_run(p, fixed, fn, fv, L)
+    with _cabi.Session(p, 700, device=0) as s:
+        for B in (700, 123, 700):
+            s.load(fixed[:B], fn[:B], fv[:B], L[:B])
+            got = s.run(B)
+            for k in want:
+                assert np.array_equal(got[k], want[k][:B]), (k, B)
+        assert s.kernel_ms > 0
