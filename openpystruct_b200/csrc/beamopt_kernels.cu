@@ -713,76 +713,7 @@ int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
                          const double *L,
                          float *I_values, double *deflections, double *rotations, float *shear,
                          float *moment, int32_t *epochs, float *loss, int32_t *status,
-                         int device, float *elapsed_ms)
-{
-    BeamConsts k;
-    int rc = make_consts(p, &k);
-    if (rc) return rc;
-    if (B < 0) return OPS_E_BADARG;
-    if (B == 0) return 0;
-    if (!fixed_uy || !L || !I_values || !deflections || !rotations || !shear || !moment || !epochs ||
-        !loss || !status)
-        return OPS_E_BADARG;
-    const size_t nn = k.nn, n = k.n, C = 1, F = (size_t)p->max_forces;
-    const size_t sz_fixed = (size_t)B * nn, sz_fn = (size_t)B * C * F * 4, sz_fv = (size_t)B * C * F * 8;
-    const size_t sz_L = (size_t)B * 8, sz_sched = (size_t)(p->max_epochs > 0 ? p->max_epochs : 1) * 8;
-    const size_t sz_I = (size_t)B * n * 4, sz_u = (size_t)B * C * nn * 8, sz_s = (size_t)B * C * n * 4;
-    const size_t sz_i32 = (size_t)B * 4;
-    unsigned char *dbuf = nullptr;
-    float *sched_h = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    size_t ws_bytes = 0, total = 0, off = 0;
-    size_t o_fixed, o_fn, o_fv, o_L, o_sched, o_I, o_defl, o_rot, o_sh, o_mo, o_ep, o_loss, o_st, o_ws;
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    OPS_CUDA(cudaSetDevice(device));
-    ws_bytes = ops_beamopt_workspace_bytes(p, B);
-    if (ws_bytes == 0) { rc = OPS_E_BADARG; goto done; }
-    o_fixed = take(sz_fixed); o_fn = take(sz_fn); o_fv = take(sz_fv); o_L = take(sz_L); o_sched = take(sz_sched);
-    o_I = take(sz_I); o_defl = take(sz_u); o_rot = take(sz_u); o_sh = take(sz_s); o_mo = take(sz_s);
-    o_ep = take(sz_i32); o_loss = take(sz_i32); o_st = take(sz_i32); o_ws = take(ws_bytes);
-    total = off;
-    sched_h = (float *)malloc(sz_sched);
-    if (!sched_h) { rc = OPS_E_BADARG; goto done; }
-    ops_beamopt_fill_schedule(p, sched_h);
-    OPS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    OPS_CUDA(cudaEventCreate(&ev0));
-    OPS_CUDA(cudaEventCreate(&ev1));
-    OPS_CUDA(cudaMallocAsync((void **)&dbuf, total, stream));
-    OPS_CUDA(cudaMemcpyAsync(dbuf + o_fixed, fixed_uy, sz_fixed, cudaMemcpyHostToDevice, stream));
-    if (F > 0) {
-        OPS_CUDA(cudaMemcpyAsync(dbuf + o_fn, force_nodes, sz_fn, cudaMemcpyHostToDevice, stream));
-        OPS_CUDA(cudaMemcpyAsync(dbuf + o_fv, force_vals, sz_fv, cudaMemcpyHostToDevice, stream));
-    }
-    OPS_CUDA(cudaMemcpyAsync(dbuf + o_L, L, sz_L, cudaMemcpyHostToDevice, stream));
-    OPS_CUDA(cudaMemcpyAsync(dbuf + o_sched, sched_h, sz_sched, cudaMemcpyHostToDevice, stream));
-    OPS_CUDA(cudaEventRecord(ev0, stream));
-    rc = ops_beamopt_launch(p, B, dbuf + o_fixed, (const int32_t *)(dbuf + o_fn), (const double *)(dbuf + o_fv),
-                            (const double *)(dbuf + o_L), (const float *)(dbuf + o_sched),
-                            (float *)(dbuf + o_I), (double *)(dbuf + o_defl), (double *)(dbuf + o_rot),
-                            (float *)(dbuf + o_sh), (float *)(dbuf + o_mo), (int32_t *)(dbuf + o_ep),
-                            (float *)(dbuf + o_loss), (int32_t *)(dbuf + o_st), dbuf + o_ws, ws_bytes, stream);
-    if (rc) goto done;
-    OPS_CUDA(cudaEventRecord(ev1, stream));
-    OPS_CUDA(cudaMemcpyAsync(I_values, dbuf + o_I, sz_I, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaMemcpyAsync(deflections, dbuf + o_defl, sz_u, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaMemcpyAsync(rotations, dbuf + o_rot, sz_u, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaMemcpyAsync(shear, dbuf + o_sh, sz_s, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaMemcpyAsync(moment, dbuf + o_mo, sz_s, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaMemcpyAsync(epochs, dbuf + o_ep, sz_i32, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaMemcpyAsync(loss, dbuf + o_loss, sz_i32, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaMemcpyAsync(status, dbuf + o_st, sz_i32, cudaMemcpyDeviceToHost, stream));
-    OPS_CUDA(cudaStreamSynchronize(stream));
-    if (elapsed_ms) OPS_CUDA(cudaEventElapsedTime(elapsed_ms, ev0, ev1));
-done:
-    if (dbuf && stream) { cudaFreeAsync(dbuf, stream); cudaStreamSynchronize(stream); }
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
-    free(sched_h);
-    if (rc > 0) cudaGetLastError();
-    return rc;
-}
+                         int device, float *elapsed_ms);
 
 struct OpsBeamOptSession {
     OpsBeamOptParams p;
@@ -901,6 +832,46 @@ void ops_beamopt_session_destroy(OpsBeamOptSession *s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
     free(s);
+}
+
+// one-shot convenience: a session for exactly this batch (allocation + pinned staging inside)
+int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
+                         const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                         const double *L,
+                         float *I_values, double *deflections, double *rotations, float *shear,
+                         float *moment, int32_t *epochs, float *loss, int32_t *status,
+                         int device, float *elapsed_ms)
+{
+    BeamConsts k;
+    int rc = make_consts(p, &k);
+    if (rc) return rc;
+    if (B < 0) return OPS_E_BADARG;
+    if (B == 0) return 0;
+    if (!fixed_uy || !L || !I_values || !deflections || !rotations || !shear || !moment || !epochs ||
+        !loss || !status || (p->max_forces > 0 && (!force_nodes || !force_vals)))
+        return OPS_E_BADARG;
+    OpsBeamOptSession *s = nullptr;
+    rc = ops_beamopt_session_create(p, B, device, &s);
+    if (rc) return rc;
+    OpsBeamOptHostArrays a;
+    ops_beamopt_session_arrays(s, &a);
+    const size_t b = (size_t)B, nn = (size_t)k.nn, n = (size_t)k.n, F = (size_t)p->max_forces;
+    memcpy(a.fixed_uy, fixed_uy, b * nn);
+    if (F > 0) { memcpy(a.force_nodes, force_nodes, b * F * 4); memcpy(a.force_vals, force_vals, b * F * 8); }
+    memcpy(a.L, L, b * 8);
+    rc = ops_beamopt_session_run(s, B, elapsed_ms);
+    if (rc == 0) {
+        memcpy(I_values, a.I_values, b * n * 4);
+        memcpy(deflections, a.deflections, b * nn * 8);
+        memcpy(rotations, a.rotations, b * nn * 8);
+        memcpy(shear, a.shear, b * n * 4);
+        memcpy(moment, a.moment, b * n * 4);
+        memcpy(epochs, a.epochs, b * 4);
+        memcpy(loss, a.loss, b * 4);
+        memcpy(status, a.status, b * 4);
+    }
+    ops_beamopt_session_destroy(s);
+    return rc;
 }
 
 }  // extern "C"
