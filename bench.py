@@ -33,12 +33,40 @@ if ROOT not in sys.path:
 
 METRIC = "optimised beams/s (fixed 600 epochs)"
 UNIT = "beams/s"
-BEAMS_PER_GPU = 10000
 EPOCHS = 600
-NUM_NODES = 101
+# BASELINE.json configs; the driver's default (and the only one `metric` is quoted on) is cfg2.  The others are
+# selected with --workload for the extra lines kept under profiles/.
+WORKLOADS = {
+    "cfg2": dict(beams=10000, num_nodes=101, num_cases=1, rollers=None,
+                 name="BASELINE configs[1]: BeamOpt_training_MultiCore dataset, 10k beams per GPU, default "
+                      "discretisation, 600 fixed epochs (early stop off)"),
+    "cfg3": dict(beams=1000000, num_nodes=101, num_cases=1, rollers=None, shard=True,
+                 name="BASELINE configs[2]: GPU-batched generation, 1M beams sharded over the ranks, default "
+                      "discretisation, 600 fixed epochs, dataset gather"),
+    "cfg4": dict(beams=100000, num_nodes=101, num_cases=8, rollers=None, shard=True,
+                 name="BASELINE configs[3]: MultiCase data, 8 load cases per beam sharing one I vector (summed "
+                      "energies), 100k beams sharded over the ranks, 600 fixed epochs"),
+    "cfg5": dict(beams=100000, num_nodes=1001, num_cases=1, rollers=[100, 300, 700, 850, 1000], shard=True,
+                 name="BASELINE configs[4]: fine discretisation, 1000-element beams (rollers x10), 100k samples "
+                      "sharded over the ranks, 600 fixed epochs"),
+}
+WL = WORKLOADS["cfg2"]
+BEAMS_PER_GPU = WL["beams"]
+NUM_NODES = WL["num_nodes"]
 # algorithmic FP64 work per beam-iteration: assembly 8n + band LDL^T 16N + solves 13N +
 # force recovery 16n = 82n + 58 with n elements, N = 2(n+1) DOFs (FMA = 2, div = sqrt = 1)
 F64_FLOP_PER_ITER = 82 * (NUM_NODES - 1) + 58
+
+
+def select_workload(name, world):
+    """Rebinds the module-level workload constants (cfg2 unless --workload says otherwise)."""
+    global WL, BEAMS_PER_GPU, NUM_NODES, F64_FLOP_PER_ITER, BYTES_PER_BEAM
+    WL = WORKLOADS[name]
+    NUM_NODES = WL["num_nodes"]
+    BEAMS_PER_GPU = WL["beams"] // world if WL.get("shard") else WL["beams"]
+    n, N, C = NUM_NODES - 1, 2 * NUM_NODES, WL["num_cases"]
+    F64_FLOP_PER_ITER = 8 * n + 16 * N + C * (13 * N + 16 * n)          # SURVEY 8d (= 82 n + 58 for C = 1)
+    BYTES_PER_BEAM = (NUM_NODES + C * 4 * 12 + 8) + (4 * n + C * (8 * n + 16 * NUM_NODES) + 12)
 # algorithmic HBM bytes per beam: inputs (fixed_uy nn + force nodes/values 4*(4+8) + L 8) and
 # outputs (I 4n, shear 4n, moment 4n, defl 8nn, rot 8nn, epochs/loss/status 12)
 BYTES_PER_BEAM = (NUM_NODES + 4 * 12 + 8) + (12 * (NUM_NODES - 1) + 16 * NUM_NODES + 12)
@@ -47,7 +75,8 @@ NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 DFMA lanes/SM x 14
 
 def workload_params(early_stop=False):
     from openpystruct_b200.params import BeamOptParams
-    return BeamOptParams.for_script("MC").replace(early_stop=early_stop, max_e=EPOCHS)
+    return BeamOptParams.for_script("MC").replace(early_stop=early_stop, max_e=EPOCHS, num_nodes=NUM_NODES,
+                                                  num_cases=WL["num_cases"])
 
 
 def sample_inputs(beams, seed):
@@ -55,9 +84,10 @@ def sample_inputs(beams, seed):
     from openpystruct_b200 import sampling
     p = workload_params()
     rng = random.Random(seed)
-    rollers, avail = sampling.fixed_bridge(p.num_nodes)
-    cases = [sampling.sample_case(p.num_nodes, 0, 200.0, rollers, avail, rng=rng) for _ in range(beams)]
-    return sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    rollers, avail = sampling.fixed_bridge(p.num_nodes, WL["rollers"])
+    cases = [sampling.sample_case(p.num_nodes, 0, 200.0, rollers, avail, rng=rng)
+             for _ in range(beams * p.num_cases)]
+    return sampling.pack_cases(p.num_nodes, p.max_forces, cases, p.num_cases)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -203,6 +233,10 @@ def run_ours(args):
     rank, local, world = init_from_env("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if args.beams > 0:
+        WORKLOADS[args.workload]["beams"] = args.beams
+        WORKLOADS[args.workload]["name"] += f" [beam count overridden: {args.beams}]"
+    select_workload(args.workload, world)
     p = workload_params()
     B = BEAMS_PER_GPU
     fixed, fn, fv, L = sample_inputs(B, seed=1000 + rank)
@@ -310,7 +344,7 @@ def run_ours(args):
     cores = host_cores()
     cpu = None
     cpu_c = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.workload == "cfg2":
         sample_beams = max(cores * 4, 16)
         rate, done, dt = cpu_torch_port(sample_beams, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -326,10 +360,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: BeamOpt_training_MultiCore dataset, 10k beams per GPU, "
-                               "default discretisation, 600 fixed epochs (early stop off)",
-                   "beams_per_gpu": B, "num_nodes": NUM_NODES, "epochs": EPOCHS, "early_stop": False,
+        "scaling": "strong" if WL.get("shard") else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WL["name"],
+                   "beams_per_gpu": B, "num_nodes": NUM_NODES, "num_cases": WL["num_cases"], "epochs": EPOCHS,
+                   "early_stop": False,
                    "fe_precision": "f64", "optimiser_precision": "f32 (torch CPU op order)",
                    "l2": "flushed between steps (256 MiB write)", "collective": "all_gather of the dataset per "
                    "step" if world > 1 else "none"},
@@ -345,7 +379,9 @@ def run_ours(args):
                                     f"nominal {NOMINAL_FP64_TFLOPS:.1f} TFLOP/s = 148 SM x 64 DFMA/clk x 1.965 GHz; "
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
-                     "kernel": "beamopt_lanes_kernel<13,100>", "kernel_ms": kernel_ms,
+                     "kernel": {"cfg2": "beamopt_lanes_kernel<13,100,1>", "cfg3": "beamopt_lanes_kernel<13,100,1>",
+                                "cfg4": "beamopt_lanes_kernel<13,0,8>", "cfg5": "beamopt_flex_kernel"}[args.workload],
+                     "kernel_ms": kernel_ms,
                      "flop_per_beam_iteration": F64_FLOP_PER_ITER,
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_achieved / hbm_peak, "bytes_per_beam": BYTES_PER_BEAM,
@@ -365,6 +401,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    ap.add_argument("--beams", type=int, default=0, help="override the workload's total beam count (exploration only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -31,11 +31,12 @@ struct OptPtrs {
 struct LanesPlan {
     int epl;             // element slots per lane (template instance)
     int nfix;            // compile-time element count of the instance (0 = run-time n)
+    int num_cases;       // load cases per beam = groups per team
     int threads, blocks;
     size_t smem_bytes;
 };
-bool lanes_supported(const BeamConsts &k);
-int lanes_plan(const BeamConsts &k, int64_t B, int sms, int smem_optin, LanesPlan *pl);
+bool lanes_supported(const BeamConsts &k, int num_cases);
+int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_optin, LanesPlan *pl);
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream);
 
 // fastmath.cuh against the compiler's IEEE operators; out4 = {div mismatches, sqrt mismatches,

@@ -342,7 +342,9 @@ static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
 {
     if (!p || p->struct_size != (int32_t)sizeof(OpsBeamOptParams)) return OPS_E_BADARG;
     if (p->num_nodes < 2 || p->num_cases < 1 || p->max_forces < 0 || p->max_epochs < 0) return OPS_E_BADARG;
-    if (p->num_cases != 1) return OPS_E_UNSUPP;
+    if (p->num_cases != 1 && !(p->solver == OPS_SOLVER_THREE_MOMENT && p->num_nodes <= 105 &&
+                                (p->num_cases == 2 || p->num_cases == 4 || p->num_cases == 8)))
+        return OPS_E_UNSUPP;       // shared-I load cases: 2, 4 or 8 per beam, lanes kernel only
     if (p->max_forces > 8) return OPS_E_UNSUPP;
     if (p->solver != OPS_SOLVER_THREE_MOMENT && p->solver != OPS_SOLVER_BAND_LDLT &&
         p->solver != OPS_SOLVER_THREE_MOMENT_THREAD)
@@ -434,7 +436,7 @@ static int plan_flex(const BeamConsts &k, int64_t B, int sms, int smem_optin, La
     return 0;
 }
 
-static int plan_launch(const BeamConsts &k, int64_t B, int solver, LaunchPlan *pl)
+static int plan_launch(const BeamConsts &k, int num_cases, int64_t B, int solver, LaunchPlan *pl)
 {
     int dev = 0, sms = 0, smem_optin = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -443,11 +445,12 @@ static int plan_launch(const BeamConsts &k, int64_t B, int solver, LaunchPlan *p
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return (int)e;
-    if (solver == OPS_SOLVER_THREE_MOMENT && lanes_supported(k)) {
+    if (solver == OPS_SOLVER_THREE_MOMENT && lanes_supported(k, num_cases)) {
         memset(pl, 0, sizeof *pl);
         pl->lanes = true;
-        return lanes_plan(k, B, sms, smem_optin, &pl->lp);
+        return lanes_plan(k, num_cases, B, sms, smem_optin, &pl->lp);
     }
+    if (num_cases != 1) return OPS_E_UNSUPP;
     if (solver == OPS_SOLVER_THREE_MOMENT || solver == OPS_SOLVER_THREE_MOMENT_THREAD)
         return plan_flex(k, B, sms, smem_optin, pl);
     const size_t pb = per_beam_bytes(k.nn);
@@ -540,7 +543,7 @@ size_t ops_beamopt_workspace_bytes(const OpsBeamOptParams *p, int64_t B)
     BeamConsts k;
     if (make_consts(p, &k) != 0 || B < 0) return 0;
     LaunchPlan pl;
-    if (plan_launch(k, B, p->solver, &pl) != 0) return 0;
+    if (plan_launch(k, p->num_cases, B, p->solver, &pl) != 0) return 0;
     return 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
 }
 
@@ -561,7 +564,7 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
         (p->max_epochs > 0 && !d_schedule))
         return OPS_E_BADARG;
     LaunchPlan pl;
-    rc = plan_launch(k, B, p->solver, &pl);
+    rc = plan_launch(k, p->num_cases, B, p->solver, &pl);
     if (rc) return rc;
     const size_t need = 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
     if (workspace_bytes < need) return OPS_E_WORKSPACE;
@@ -735,7 +738,7 @@ int ops_beamopt_session_create(const OpsBeamOptParams *p, int64_t max_beams, int
     OpsBeamOptSession *s = (OpsBeamOptSession *)calloc(1, sizeof *s);
     if (!s) return OPS_E_BADARG;
     s->p = *p; s->max_beams = max_beams; s->device = device;
-    const size_t B = (size_t)max_beams, nn = k.nn, n = k.n, C = 1, F = (size_t)p->max_forces;
+    const size_t B = (size_t)max_beams, nn = k.nn, n = k.n, C = (size_t)p->num_cases, F = (size_t)p->max_forces;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     // inputs first (one contiguous H2D range), then outputs (one contiguous D2H range), then device-only
@@ -787,7 +790,8 @@ int ops_beamopt_session_run(OpsBeamOptSession *s, int64_t B, float *elapsed_ms)
     if (!s || B < 0 || B > s->max_beams) return OPS_E_BADARG;
     if (B == 0) return 0;
     int rc = 0;
-    const size_t nn = (size_t)s->p.num_nodes, n = nn - 1, F = (size_t)s->p.max_forces, b = (size_t)B;
+    const size_t nn = (size_t)s->p.num_nodes, n = nn - 1, C = (size_t)s->p.num_cases;
+    const size_t F = (size_t)s->p.max_forces * C, b = (size_t)B;
     unsigned char *d = s->dbuf, *h = s->hbuf;
     auto h2d = [&](size_t o, size_t bytes) { return cudaMemcpyAsync(d + o, h + o, bytes, cudaMemcpyHostToDevice, s->stream); };
     auto d2h = [&](size_t o, size_t bytes) { return cudaMemcpyAsync(h + o, d + o, bytes, cudaMemcpyDeviceToHost, s->stream); };
@@ -810,8 +814,8 @@ int ops_beamopt_session_run(OpsBeamOptSession *s, int64_t B, float *elapsed_ms)
     if (B == s->max_beams) {
         OPS_CUDA(d2h(s->in_bytes, s->out_bytes));
     } else {
-        OPS_CUDA(d2h(s->o_I, b * n * 4)); OPS_CUDA(d2h(s->o_defl, b * nn * 8)); OPS_CUDA(d2h(s->o_rot, b * nn * 8));
-        OPS_CUDA(d2h(s->o_sh, b * n * 4)); OPS_CUDA(d2h(s->o_mo, b * n * 4));
+        OPS_CUDA(d2h(s->o_I, b * n * 4)); OPS_CUDA(d2h(s->o_defl, b * C * nn * 8)); OPS_CUDA(d2h(s->o_rot, b * C * nn * 8));
+        OPS_CUDA(d2h(s->o_sh, b * C * n * 4)); OPS_CUDA(d2h(s->o_mo, b * C * n * 4));
         OPS_CUDA(d2h(s->o_ep, b * 4)); OPS_CUDA(d2h(s->o_loss, b * 4)); OPS_CUDA(d2h(s->o_st, b * 4));
     }
     OPS_CUDA(cudaStreamSynchronize(s->stream));
@@ -855,17 +859,18 @@ int ops_beamopt_run_host(const OpsBeamOptParams *p, int64_t B,
     if (rc) return rc;
     OpsBeamOptHostArrays a;
     ops_beamopt_session_arrays(s, &a);
-    const size_t b = (size_t)B, nn = (size_t)k.nn, n = (size_t)k.n, F = (size_t)p->max_forces;
+    const size_t b = (size_t)B, nn = (size_t)k.nn, n = (size_t)k.n, C = (size_t)p->num_cases;
+    const size_t F = (size_t)p->max_forces * C;
     memcpy(a.fixed_uy, fixed_uy, b * nn);
     if (F > 0) { memcpy(a.force_nodes, force_nodes, b * F * 4); memcpy(a.force_vals, force_vals, b * F * 8); }
     memcpy(a.L, L, b * 8);
     rc = ops_beamopt_session_run(s, B, elapsed_ms);
     if (rc == 0) {
         memcpy(I_values, a.I_values, b * n * 4);
-        memcpy(deflections, a.deflections, b * nn * 8);
-        memcpy(rotations, a.rotations, b * nn * 8);
-        memcpy(shear, a.shear, b * n * 4);
-        memcpy(moment, a.moment, b * n * 4);
+        memcpy(deflections, a.deflections, b * C * nn * 8);
+        memcpy(rotations, a.rotations, b * C * nn * 8);
+        memcpy(shear, a.shear, b * C * n * 4);
+        memcpy(moment, a.moment, b * C * n * 4);
         memcpy(epochs, a.epochs, b * 4);
         memcpy(loss, a.loss, b * 4);
         memcpy(status, a.status, b * 4);

@@ -25,7 +25,16 @@ using namespace lanes;
 #endif
 constexpr int LANES_MAX_THREADS = OPS_LANES_MAXT;
 
-template <int EPL, int NFIX>
+// synchronisation of the NC groups of a team: one warp (NC <= 4) or 8 NC / 32 whole warps (named barrier)
+template <int NC>
+__device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
+{
+    if (NC == 1) return;
+    if (NC * LPB <= 32) __syncwarp(team_mask);
+    else asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "n"(NC * LPB) : "memory");
+}
+
+template <int EPL, int NFIX, int NC>
 __global__ void __launch_bounds__(LANES_MAX_THREADS, 1)
 beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 {
@@ -33,11 +42,15 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     const int T = blockDim.x, G = T / LPB;
     const int tid = threadIdx.x, l = tid & (LPB - 1), g = tid / LPB;
     const unsigned gmask = 0xffu << (tid & 24);
+    const int case_id = g % NC;                                    // load case of this group
+    const unsigned team_mask = (NC * LPB >= 32) ? 0xffffffffu
+                                                : (((1u << (NC * LPB)) - 1u) << ((tid & 31) / (NC * LPB) * (NC * LPB)));
+    const int barrier_id = 1 + g / NC;                             // named barrier of the team (NC = 8)
     const int n = NFIX ? NFIX : k.n;
     const int nn = n + 1;
 
     double *lane_d = reinterpret_cast<double *>(smem_raw);
-    double *tab_d = lane_d + (size_t)lane_doubles(EPL) * T;
+    double *tab_d = lane_d + (size_t)lane_doubles(EPL, NC) * T;
     double *grp_d = tab_d + (size_t)TAB_SLOTS * G;
     int *grp_i = reinterpret_cast<int *>(grp_d + (size_t)GROUP_DOUBLES * G);
     LaneStore ls;
@@ -45,6 +58,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     ls.gq = reinterpret_cast<Pair *>(lane_d) + tid;
     ls.mq = ls.gq + (size_t)EPL * T;
     ls.scr = lane_d + (size_t)4 * EPL * T + tid;
+    ls.xc = reinterpret_cast<PairF *>(lane_d + (size_t)(4 * EPL + SCR_SLOTS) * T) + tid;
     GroupStore gs;
     gs.gs = G;
     gs.tab = tab_d + (size_t)TAB_SLOTS * g;
@@ -53,6 +67,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     gs.gd = gs.fs.sd + (size_t)FlexStore::NUM_DOUBLES * G;
     gs.fs.si = grp_i + g;
     gs.gi = gs.fs.si + (size_t)FlexStore::NUM_INTS * G;
+    int *team_gi = gs.gi - case_id;                                // the case-0 group's ints
 
     LaneRegs<EPL> rg;
     FlexBeam fb;
@@ -65,18 +80,30 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     while (true) {
         if (!have && !exhausted) {
             long long nb = 0;
-            if (l == 0) nb = (long long)atomicAdd(p.counter, 1ULL);
-            nb = __shfl_sync(gmask, nb, 0, LPB);
+            if (NC == 1) {
+                if (l == 0) nb = (long long)atomicAdd(p.counter, 1ULL);
+                nb = __shfl_sync(gmask, nb, 0, LPB);
+            } else {
+                if (case_id == 0 && l == 0) {
+                    nb = (long long)atomicAdd(p.counter, 1ULL);
+                    team_gi[4 * G] = (int)(nb & 0xffffffffLL);
+                    team_gi[5 * G] = (int)(nb >> 32);
+                }
+                team_sync<NC>(team_mask, barrier_id);
+                nb = ((long long)team_gi[5 * G] << 32) | (unsigned int)team_gi[4 * G];
+                team_sync<NC>(team_mask, barrier_id);
+            }
             if (nb < B) {
                 b = nb;
                 have = true;
                 t = 0; counter = 0; best = INFINITY; lossf = NAN;
+                const long long bc = b * NC + case_id;             // row of this group's load case
                 if (l == 0) {
                     int fnode[FLEX_MAXF];
                     double fval[FLEX_MAXF];
                     for (int j = 0; j < k.max_forces; ++j) {
-                        fnode[j] = p.force_nodes[b * k.max_forces + j];
-                        fval[j] = p.force_vals[b * k.max_forces + j];
+                        fnode[j] = p.force_nodes[bc * k.max_forces + j];
+                        fval[j] = p.force_vals[bc * k.max_forces + j];
                     }
                     const uint8_t *fx = p.fixed_uy + b * nn;
                     FlexBeam f0;
@@ -109,8 +136,13 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                 __syncwarp(gmask);
                 const int rc = group_solve(fb, gs, l);
                 __syncwarp(gmask);
-                lane_forces<EPL>(k, n, rg, ls, gs, l);
-                __syncwarp(gmask);
+                if (NC > 1) {
+                    lane_case_squares<EPL>(rg, ls, gs);
+                    team_sync<NC>(team_mask, barrier_id);
+                }
+                lane_forces<EPL, NC>(k, n, rg, ls, gs, l, case_id);
+                if (NC > 1) team_sync<NC>(team_mask, barrier_id);   // exchange columns are rewritten next epoch
+                else __syncwarp(gmask);
                 lossf = group_loss(k, n, ls, l);
                 ++t;
                 if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
@@ -126,17 +158,20 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             } else {
                 // record of the beam: fields of the last analysed inertias, then the last Adam step
                 const bool fields = (t > 0) && (bad == 0);
-                lane_emit_forces<EPL>(n, rg, ls, gs, l, fields, p.shear + b * n, p.moment + b * n);
+                const long long bc = b * NC + case_id;
+                lane_emit_forces<EPL>(n, rg, ls, gs, l, fields, p.shear + bc * n, p.moment + bc * n);
                 __syncwarp(gmask);
                 if (l == 0) {
                     LaneStore ls0 = ls;
-                    group_emit_displacements(k, fb, ls0, gs, fields, p.defl + b * nn, p.rot + b * nn);
-                    p.epochs[b] = t;
-                    p.loss[b] = lossf;
-                    p.status[b] = bad;
+                    group_emit_displacements(k, fb, ls0, gs, fields, p.defl + bc * nn, p.rot + bc * nn);
+                    if (case_id == 0) {
+                        p.epochs[b] = t;
+                        p.loss[b] = lossf;
+                        p.status[b] = bad;
+                    }
                 }
                 if (t > 0) lane_adam<EPL, false>(k, rg, ls, neg_step, bc2_sqrt);
-                lane_emit_inertias<EPL>(n, rg, l, p.I_values + b * n);
+                if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + b * n);
                 __syncwarp(gmask);
                 have = false;
             }
@@ -144,9 +179,10 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     }
 }
 
-bool lanes_supported(const BeamConsts &k)
+bool lanes_supported(const BeamConsts &k, int num_cases)
 {
-    return k.n >= 1 && k.n <= 8 * 21 && k.max_forces <= FLEX_MAXF;
+    const bool cases_ok = num_cases == 1 || num_cases == 2 || num_cases == 4 || num_cases == 8;
+    return cases_ok && k.n >= 1 && k.n <= 8 * 21 && k.max_forces <= FLEX_MAXF && (num_cases == 1 || k.n <= 104);
 }
 
 static int pick_epl(int n)
@@ -157,21 +193,25 @@ static int pick_epl(int n)
     return 21;
 }
 
-int lanes_plan(const BeamConsts &k, int64_t B, int sms, int smem_optin, LanesPlan *pl)
+int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_optin, LanesPlan *pl)
 {
     pl->epl = pick_epl(k.n);
     pl->nfix = (k.n == 100) ? 100 : 0;
-    const size_t per_group = (size_t)LPB * 8 * lane_doubles(pl->epl) + (size_t)(TAB_SLOTS + GROUP_DOUBLES) * 8 +
+    pl->num_cases = num_cases;
+    const size_t per_group = (size_t)LPB * 8 * lane_doubles(pl->epl, num_cases) + (size_t)(TAB_SLOTS + GROUP_DOUBLES) * 8 +
                              (size_t)GROUP_INTS * 4;
     int groups = (int)((size_t)smem_optin / per_group);
     int T = groups * LPB / 32 * 32;
     if (T > LANES_MAX_THREADS) T = LANES_MAX_THREADS;
     const char *thr_env = getenv("OPS_LANES_THREADS");            // profiling knob
     if (thr_env && atoi(thr_env) >= 32 && atoi(thr_env) <= T) T = atoi(thr_env) / 32 * 32;
-    if (T < 32) return -2;
+    const int team_threads = num_cases * LPB;                     // whole teams per CTA (and whole warps per team)
+    const int quantum = team_threads > 32 ? team_threads : 32;
+    T = T / quantum * quantum;
+    if (T < quantum) return -2;
     pl->threads = T;
     pl->smem_bytes = per_group * (T / LPB);
-    const long per_cta = T / LPB;
+    const long per_cta = T / team_threads;
     long want = (long)((B + per_cta - 1) / per_cta);
     pl->blocks = (int)(want < sms ? want : sms);
     if (pl->blocks < 1) pl->blocks = 1;
@@ -182,11 +222,11 @@ int lanes_plan(const BeamConsts &k, int64_t B, int sms, int smem_optin, LanesPla
     return 0;
 }
 
-template <int EPL, int NFIX>
+template <int EPL, int NFIX, int NC>
 static cudaError_t launch_instance(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl,
                                    cudaStream_t stream)
 {
-    auto kern = beamopt_lanes_kernel<EPL, NFIX>;
+    auto kern = beamopt_lanes_kernel<EPL, NFIX, NC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<pl.blocks, pl.threads, pl.smem_bytes, stream>>>(k, B, p);
@@ -195,12 +235,27 @@ static cudaError_t launch_instance(const BeamConsts &k, long long B, const OptPt
 
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream)
 {
-    if (pl.nfix == 100) return launch_instance<13, 100>(k, B, p, pl, stream);
+    if (pl.num_cases > 1) {
+        // load cases sharing one inertia vector: the 100-element discretisation and the generic <= 104-element one
+        switch (pl.num_cases * 100 + pl.epl) {
+        case 204: return launch_instance<4, 0, 2>(k, B, p, pl, stream);
+        case 208: return launch_instance<8, 0, 2>(k, B, p, pl, stream);
+        case 213: return launch_instance<13, 0, 2>(k, B, p, pl, stream);
+        case 404: return launch_instance<4, 0, 4>(k, B, p, pl, stream);
+        case 408: return launch_instance<8, 0, 4>(k, B, p, pl, stream);
+        case 413: return launch_instance<13, 0, 4>(k, B, p, pl, stream);
+        case 804: return launch_instance<4, 0, 8>(k, B, p, pl, stream);
+        case 808: return launch_instance<8, 0, 8>(k, B, p, pl, stream);
+        case 813: return launch_instance<13, 0, 8>(k, B, p, pl, stream);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    if (pl.nfix == 100) return launch_instance<13, 100, 1>(k, B, p, pl, stream);
     switch (pl.epl) {
-    case 4: return launch_instance<4, 0>(k, B, p, pl, stream);
-    case 8: return launch_instance<8, 0>(k, B, p, pl, stream);
-    case 13: return launch_instance<13, 0>(k, B, p, pl, stream);
-    default: return launch_instance<21, 0>(k, B, p, pl, stream);
+    case 4: return launch_instance<4, 0, 1>(k, B, p, pl, stream);
+    case 8: return launch_instance<8, 0, 1>(k, B, p, pl, stream);
+    case 13: return launch_instance<13, 0, 1>(k, B, p, pl, stream);
+    default: return launch_instance<21, 0, 1>(k, B, p, pl, stream);
     }
 }
 

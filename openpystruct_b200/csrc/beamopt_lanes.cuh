@@ -24,6 +24,12 @@
 //     Mc_e = M0_e + MS_l + (MS_r - MS_l) d ke ,   V_e = Q0_e + (MS_r - MS_l) d / Le
 // followed by the fp32 loss terms, the frozen-M,V gradient and the Adam update of its elements.
 //
+// Load cases sharing one inertia vector (not in the reference): the NC cases of a beam
+// run on NC adjacent groups (a "team").  Every group carries the same I, m, v and the coefficients of its
+// own case; after PASS 2's forces the groups exchange M^2, V^2 through shared memory, add them in case
+// order (c_0 + c_1 + ..., a fixed order) and then compute identical gradients, losses, Adam
+// steps and stop decisions -- the team stays in lockstep without any further communication.
+//
 // All cross-lane traffic goes through shared memory + __syncwarp(group mask), so the phase functions
 // below contain no CUDA intrinsics and tests/hostsim runs the very same code lane by lane on the host.
 #pragma once
@@ -43,11 +49,11 @@ constexpr int SCR_SLOTS = SCR_STAGE + 3;
 constexpr int TAB_T2 = 2 * (NSPAN + 1);         // span table: Pair {MS_l, (MS_r - MS_l) d} [6], then (MS_r - MS_l) d / Le [6]
 constexpr int TAB_SLOTS = 3 * (NSPAN + 1) + 2;  // contiguous per group; +2 keeps the four groups of a warp on distinct banks
 constexpr int GX_DOUBLES = 2;                   // Moh, Qoh
-constexpr int GX_INTS = 4;                      // m, last, nloads, setup status
+constexpr int GX_INTS = 6;                      // m, last, nloads, setup status, beam index of the team (lo, hi)
 constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + GX_DOUBLES;   // strided [slot][group] columns (+ TAB_SLOTS contiguous)
 constexpr int GROUP_INTS = FlexStore::NUM_INTS + GX_INTS;
 
-OPS_HD constexpr int lane_doubles(int epl) { return 4 * epl + SCR_SLOTS; }
+OPS_HD constexpr int lane_doubles(int epl, int nc) { return 4 * epl + SCR_SLOTS + (nc > 1 ? epl : 0); }
 
 template <int EPL>
 struct LaneRegs {
@@ -61,10 +67,15 @@ struct alignas(16) Pair {                       // two doubles moved with one 12
 };
 
 // per-lane shared columns, entry k at base[k * ls]
+struct alignas(8) PairF {                       // {M^2, V^2} of one load case, fp32
+    float c, h;
+};
+
 struct LaneStore {
     Pair *gq;                                   // [EPL]: {G, Q} coefficients of the element
     Pair *mq;                                   // [EPL]: {M0, Q0} of the element
     double *scr;                                // [SCR_SLOTS]
+    PairF *xc;                                  // [EPL] (multi-case kernels only): squares exchanged between the case groups
     long ls;
 };
 
@@ -344,30 +355,60 @@ OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const G
 #endif
 constexpr int NB = OPS_LANES_NB;
 
+// multi-case kernels, before PASS 2: M^2, V^2 of this group's load case into the exchange column
+template <int EPL>
+OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs)
+{
+#pragma unroll
+    for (int kk = 0; kk < EPL; ++kk) {
+        double Mc, Qv;
+        element_forces<EPL>(rg, ls, gs, kk, Mc, Qv);
+        const float Mf = (float)Mc, Vf = (float)Qv;
+        PairF x;
+        x.c = Mf * Mf; x.h = Vf * Vf;
+        ls.xc[(long)kk * ls.ls] = x;
+    }
+}
+
 // PASS 2: end forces, loss terms d, q and autograd's gradient with M, V constant (element_update_f32,
 // first half; the gradient is kept in rg.g), torch.sum partials of sum I, sum d, sum q.
+// NC > 1: the squares come from the exchange columns of the team (case_id = this group's case).
 // fp32 ranges for the branch-free division / square root: I in [clamp_min, 1e20) (the clamp,
 // SingleCore:208), c = M^2 and h = V^2 zero or >= 2^-100.
-template <int EPL>
-OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, int l)
+template <int EPL, int NC>
+OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, int l,
+                        int case_id)
 {
     const SumShape sh = sum_shape(n);
     float aI[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ad[4] = {0.0f, 0.0f, 0.0f, 0.0f}, aq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float tI = 0.0f, td = 0.0f, tq = 0.0f;
+    const PairF *x0 = ls.xc - (long)case_id * LPB;             // this lane's column in the team's case-0 group
 #pragma unroll
     for (int k0 = 0; k0 < EPL; k0 += NB) {
         double Mc[NB], Qv[NB];
         float c[NB], h[NB], b[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB];
+        if (NC == 1) {
 #pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (k0 + i < EPL) element_forces<EPL>(rg, ls, gs, k0 + i, Mc[i], Qv[i]);
+            for (int i = 0; i < NB; ++i)
+                if (k0 + i < EPL) element_forces<EPL>(rg, ls, gs, k0 + i, Mc[i], Qv[i]);
+        }
 #pragma unroll
         for (int i = 0; i < NB; ++i)
             if (k0 + i < EPL) {
                 const float I = rg.I[k0 + i];
-                const float Mf = (float)Mc[i], Vf = (float)Qv[i];
-                c[i] = Mf * Mf;
-                h[i] = Vf * Vf;
+                if (NC == 1) {
+                    const float Mf = (float)Mc[i], Vf = (float)Qv[i];
+                    c[i] = Mf * Mf;
+                    h[i] = Vf * Vf;
+                } else {
+                    PairF x = x0[(long)(k0 + i) * ls.ls];
+                    c[i] = x.c; h[i] = x.h;
+#pragma unroll
+                    for (int cc = 1; cc < NC; ++cc) {
+                        x = x0[(long)(k0 + i) * ls.ls + cc * LPB];
+                        c[i] += x.c; h[i] += x.h;
+                    }
+                }
                 b[i] = k.E2 * I + k.epsf;
                 y[i] = fm::rsq_a(I);
                 rb[i] = fm::rcp_a(b[i]);

@@ -41,19 +41,48 @@ def shard_inputs(inputs: Dict[str, torch.Tensor], rank: int, world: int) -> Tupl
     return out, stop - start
 
 
+_gather_buffers: Dict[tuple, torch.Tensor] = {}
+
+
 def gather_outputs(local: Dict[str, torch.Tensor], num_beams: int, group=None) -> Dict[str, torch.Tensor]:
-    """all_gather_into_tensor of every output (equal per-rank blocks), trimmed to num_beams."""
+    """The dataset gather: every rank's block of every output in ONE collective.  The per-rank tensors are
+    packed into one byte buffer (256-byte aligned segments), gathered with a single
+    ``all_gather_into_tensor`` into a reused [world, bytes] buffer and handed back as typed views,
+    trimmed to ``num_beams``."""
     world = dist.get_world_size(group)
+    names = list(local)
+    dev = local[names[0]].device
+    segs, off = [], 0
+    for k in names:
+        t = local[k]
+        nbytes = t.numel() * t.element_size()
+        segs.append((k, off, nbytes, t.dtype, tuple(t.shape)))
+        off += (nbytes + 255) // 256 * 256
+    total = max(off, 256)
+    key = (str(dev), world, total, id(group))
+    bufs = _gather_buffers.get(key)
+    if bufs is None:
+        bufs = (torch.empty(total, dtype=torch.uint8, device=dev),
+                torch.empty((world, total), dtype=torch.uint8, device=dev))
+        _gather_buffers.clear()                      # one live shape at a time
+        _gather_buffers[key] = bufs
+    send, recv = bufs
+    for k, o, nbytes, _, _ in segs:
+        if nbytes:
+            send[o:o + nbytes].copy_(local[k].contiguous().view(-1).view(torch.uint8))
+    if dist.get_backend(group) == "gloo":
+        dist.all_gather(list(recv.unbind(0)), send, group=group)
+    else:
+        dist.all_gather_into_tensor(recv, send, group=group)
     out = {}
-    for k, t in local.items():
-        t = t.contiguous()
-        full = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        if dist.get_backend(group) == "gloo":
-            parts = list(full.chunk(world, dim=0))
-            dist.all_gather(parts, t, group=group)
-        else:
-            dist.all_gather_into_tensor(full, t, group=group)
-        out[k] = full[:num_beams]
+    for k, o, nbytes, dtype, shape in segs:
+        per = shape[0]
+        if nbytes == 0:
+            out[k] = torch.empty((0,) + shape[1:], dtype=dtype, device=dev)
+            continue
+        blocks = recv[:, o:o + nbytes].view(dtype).reshape((world * per,) + shape[1:]) if world == 1 else \
+            recv[:, o:o + nbytes].contiguous().view(dtype).reshape((world * per,) + shape[1:])
+        out[k] = blocks[:num_beams]
     return out
 
 

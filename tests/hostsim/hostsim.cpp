@@ -217,7 +217,7 @@ extern "C" int hostsim_beamsolve_flex(const OpsBeamOptParams *p, int64_t B, cons
 // __syncwarp points of the kernel are the boundaries between the lane loops.
 #include "../../openpystruct_b200/csrc/beamopt_lanes.cuh"
 
-template <int EPL>
+template <int EPL, int NC>
 static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, const int32_t *force_nodes,
                      const double *force_vals, const double *L, const float *sched, float *I_values,
                      double *defl, double *rot, float *shear, float *moment, int32_t *epochs, float *loss,
@@ -225,44 +225,51 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
 {
     using namespace ops::lanes;
     const int n = k.n, nn = k.nn;
-    std::vector<Pair> lane_p((size_t)2 * EPL * LPB);
-    std::vector<double> lane_s((size_t)SCR_SLOTS * LPB), grp_d(GROUP_DOUBLES);
-    std::vector<Pair> tab_p(TAB_SLOTS / 2);
-    std::vector<int> grp_i(GROUP_INTS);
-    LaneStore ls[LPB];
-    for (int l = 0; l < LPB; ++l) {
-        ls[l].ls = LPB;
-        ls[l].gq = lane_p.data() + l;
-        ls[l].mq = ls[l].gq + (size_t)EPL * LPB;
-        ls[l].scr = lane_s.data() + l;
-    }
-    GroupStore gs;
-    gs.gs = 1;
-    gs.tab = reinterpret_cast<double *>(tab_p.data());
-    gs.fs.sd = grp_d.data(); gs.fs.stride = 1;
-    gs.gd = gs.fs.sd + FlexStore::NUM_DOUBLES;
-    gs.fs.si = grp_i.data();
-    gs.gi = gs.fs.si + FlexStore::NUM_INTS;
-    for (int64_t b = 0; b < B; ++b) {
-        LaneRegs<EPL> rg[LPB];
-        FlexBeam fb;
-        int fnode[FLEX_MAXF];
-        double fval[FLEX_MAXF];
-        for (int j = 0; j < k.max_forces; ++j) {
-            fnode[j] = force_nodes[b * k.max_forces + j];
-            fval[j] = force_vals[b * k.max_forces + j];
-        }
-        const uint8_t *fx = fixed_uy + b * nn;
-        {
-            FlexBeam f0;
-            const int rc = flex_setup(k, L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode, fval, gs.fs, f0);
-            group_publish(f0, rc, gs);
-            group_table_init(gs);
-        }
-        int bad = group_fetch(k, L[b], gs, fb);
+    constexpr int TL = NC * LPB;                       // lanes of a team; column index = case * 8 + lane
+    std::vector<Pair> lane_p((size_t)2 * EPL * TL);
+    std::vector<double> lane_s((size_t)SCR_SLOTS * TL), grp_d((size_t)GROUP_DOUBLES * NC);
+    std::vector<PairF> lane_x((size_t)EPL * TL);
+    std::vector<Pair> tab_p((size_t)TAB_SLOTS / 2 * NC);
+    std::vector<int> grp_i((size_t)GROUP_INTS * NC);
+    LaneStore ls[NC][LPB];
+    GroupStore gs[NC];
+    for (int c = 0; c < NC; ++c) {
         for (int l = 0; l < LPB; ++l) {
-            if (!bad) { lane_init<EPL>(k, n, fb, gs, ls[l], l, rg[l]); lane_pass1<EPL>(rg[l], ls[l]); }
-            else lane_reset<EPL>(k, rg[l]);
+            const int col = c * LPB + l;
+            ls[c][l].ls = TL;
+            ls[c][l].gq = lane_p.data() + col;
+            ls[c][l].mq = ls[c][l].gq + (size_t)EPL * TL;
+            ls[c][l].scr = lane_s.data() + col;
+            ls[c][l].xc = lane_x.data() + col;
+        }
+        gs[c].gs = NC;
+        gs[c].tab = reinterpret_cast<double *>(tab_p.data()) + (size_t)TAB_SLOTS * c;
+        gs[c].fs.sd = grp_d.data() + c; gs[c].fs.stride = NC;
+        gs[c].gd = gs[c].fs.sd + (size_t)FlexStore::NUM_DOUBLES * NC;
+        gs[c].fs.si = grp_i.data() + c;
+        gs[c].gi = gs[c].fs.si + (size_t)FlexStore::NUM_INTS * NC;
+    }
+    for (int64_t b = 0; b < B; ++b) {
+        static LaneRegs<EPL> rg[NC][LPB];
+        FlexBeam fb[NC];
+        int bad = 0;
+        const uint8_t *fx = fixed_uy + b * nn;
+        for (int c = 0; c < NC; ++c) {
+            int fnode[FLEX_MAXF];
+            double fval[FLEX_MAXF];
+            for (int j = 0; j < k.max_forces; ++j) {
+                fnode[j] = force_nodes[(b * NC + c) * k.max_forces + j];
+                fval[j] = force_vals[(b * NC + c) * k.max_forces + j];
+            }
+            FlexBeam f0;
+            const int rc = flex_setup(k, L[b], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode, fval, gs[c].fs, f0);
+            group_publish(f0, rc, gs[c]);
+            group_table_init(gs[c]);
+            bad = group_fetch(k, L[b], gs[c], fb[c]);
+            for (int l = 0; l < LPB; ++l) {
+                if (!bad) { lane_init<EPL>(k, n, fb[c], gs[c], ls[c][l], l, rg[c][l]); lane_pass1<EPL>(rg[c][l], ls[c][l]); }
+                else lane_reset<EPL>(k, rg[c][l]);
+            }
         }
         int t = 0, counter = 0;
         double best = INFINITY;
@@ -270,14 +277,20 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
         bool done = (k.max_epochs <= 0) || bad;
         while (!done) {
             neg_step = sched[2 * t]; bc2_sqrt = sched[2 * t + 1];
-            for (int l = 0; l < LPB; ++l) lane_reduce(l, fb.m, ls[l], gs);
             int rc = 0;
-            for (int l = LPB - 1; l >= 0; --l) rc = group_solve(fb, gs, l);
-            for (int l = 0; l < LPB; ++l) lane_forces<EPL>(k, n, rg[l], ls[l], gs, l);
-            float lv[LPB];
-            for (int l = 0; l < LPB; ++l) lv[l] = group_loss(k, n, ls[l], l);
-            for (int l = 1; l < LPB; ++l) if (memcmp(&lv[l], &lv[0], 4) != 0) return -100;   // lanes must agree
-            lossf = lv[0];
+            for (int c = 0; c < NC; ++c) {
+                for (int l = 0; l < LPB; ++l) lane_reduce(l, fb[c].m, ls[c][l], gs[c]);
+                for (int l = LPB - 1; l >= 0; --l) rc |= group_solve(fb[c], gs[c], l);
+                if (NC > 1) for (int l = 0; l < LPB; ++l) lane_case_squares<EPL>(rg[c][l], ls[c][l], gs[c]);
+            }
+            float lv[NC][LPB];
+            for (int c = 0; c < NC; ++c)
+                for (int l = 0; l < LPB; ++l) lane_forces<EPL, NC>(k, n, rg[c][l], ls[c][l], gs[c], l, c);
+            for (int c = 0; c < NC; ++c)
+                for (int l = 0; l < LPB; ++l) lv[c][l] = group_loss(k, n, ls[c][l], l);
+            for (int c = 0; c < NC; ++c)
+                for (int l = 0; l < LPB; ++l) if (memcmp(&lv[c][l], &lv[0][0], 4) != 0) return -100;   // the team must agree
+            lossf = lv[0][0];
             ++t;
             if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
             if (k.early_stop) {
@@ -286,17 +299,22 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
                 if (counter >= k.patience) done = true;
             }
             if (t >= k.max_epochs) done = true;
-            if (!done) for (int l = 0; l < LPB; ++l) lane_adam<EPL, true>(k, rg[l], ls[l], neg_step, bc2_sqrt);
+            if (!done)
+                for (int c = 0; c < NC; ++c)
+                    for (int l = 0; l < LPB; ++l) lane_adam<EPL, true>(k, rg[c][l], ls[c][l], neg_step, bc2_sqrt);
         }
         const bool fields = (t > 0) && (bad == 0);
-        for (int l = 0; l < LPB; ++l)
-            lane_emit_forces<EPL>(n, rg[l], ls[l], gs, l, fields, shear + b * n, moment + b * n);
-        group_emit_displacements(k, fb, ls[0], gs, fields, defl + b * nn, rot + b * nn);
-        epochs[b] = t; loss[b] = lossf; status[b] = bad;
-        for (int l = 0; l < LPB; ++l) {
-            if (t > 0) lane_adam<EPL, false>(k, rg[l], ls[l], neg_step, bc2_sqrt);
-            lane_emit_inertias<EPL>(n, rg[l], l, I_values + b * n);
+        for (int c = 0; c < NC; ++c) {
+            const int64_t bc = b * NC + c;
+            for (int l = 0; l < LPB; ++l)
+                lane_emit_forces<EPL>(n, rg[c][l], ls[c][l], gs[c], l, fields, shear + bc * n, moment + bc * n);
+            group_emit_displacements(k, fb[c], ls[c][0], gs[c], fields, defl + bc * nn, rot + bc * nn);
+            for (int l = 0; l < LPB; ++l) {
+                if (t > 0) lane_adam<EPL, false>(k, rg[c][l], ls[c][l], neg_step, bc2_sqrt);
+                if (c == 0) lane_emit_inertias<EPL>(n, rg[c][l], l, I_values + b * n);
+            }
         }
+        epochs[b] = t; loss[b] = lossf; status[b] = bad;
     }
     return 0;
 }
@@ -306,15 +324,21 @@ extern "C" int hostsim_beamopt_lanes(const OpsBeamOptParams *p, int64_t B, const
                                      const float *sched, float *I_values, double *defl, double *rot,
                                      float *shear, float *moment, int32_t *epochs, float *loss, int32_t *status)
 {
-    if (p->num_cases != 1 || p->max_forces > FLEX_MAXF) return OPS_E_UNSUPP;
+    if (p->max_forces > FLEX_MAXF) return OPS_E_UNSUPP;
     BeamConsts k;
     consts_from(p, &k);
-#define RUN(EPL) lanes_run<EPL>(k, B, fixed_uy, force_nodes, force_vals, L, sched, I_values, defl, rot, shear, \
-                                moment, epochs, loss, status)
-    if (k.n <= 32) return RUN(4);
-    if (k.n <= 64) return RUN(8);
-    if (k.n <= 104) return RUN(13);
-    if (k.n <= 168) return RUN(21);
+#define RUN(EPL, NC) lanes_run<EPL, NC>(k, B, fixed_uy, force_nodes, force_vals, L, sched, I_values, defl, rot, shear, \
+                                        moment, epochs, loss, status)
+    if (p->num_cases == 1) {
+        if (k.n <= 32) return RUN(4, 1);
+        if (k.n <= 64) return RUN(8, 1);
+        if (k.n <= 104) return RUN(13, 1);
+        if (k.n <= 168) return RUN(21, 1);
+    } else if (k.n <= 104) {
+        if (p->num_cases == 2) return k.n <= 32 ? RUN(4, 2) : (k.n <= 64 ? RUN(8, 2) : RUN(13, 2));
+        if (p->num_cases == 4) return k.n <= 32 ? RUN(4, 4) : (k.n <= 64 ? RUN(8, 4) : RUN(13, 4));
+        if (p->num_cases == 8) return k.n <= 32 ? RUN(4, 8) : (k.n <= 64 ? RUN(8, 8) : RUN(13, 8));
+    }
 #undef RUN
     return OPS_E_UNSUPP;
 }

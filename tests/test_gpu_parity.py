@@ -305,3 +305,35 @@ def test_session_matches_the_device_pointer_entry():
             for k in want:
                 assert np.array_equal(got[k], want[k][:B]), (k, B)
         assert s.kernel_ms > 0
+
+
+@pytest.mark.parametrize("num_cases", [2, 4, 8])
+def test_shared_inertia_load_cases(num_cases):
+    """BASELINE config 4 (extension): C load cases per beam share one I vector, summed
+    energies; one record per (beam, case) with identical I_values."""
+    p = BeamOptParams.for_script("MC").replace(num_cases=num_cases)
+    B = 96
+    cases = seeded_cases(p, B * num_cases, seed=107)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases, num_cases)
+    a, b = oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L)
+    assert not b["status"].any()
+    same = a["epochs"] == b["epochs"]
+    assert same.mean() >= 0.98
+    assert np.max(np.abs(a["I"][same] - b["I"][same]) / a["I"][same]) < 1e-5
+    assert (a["loss"][same] == b["loss"][same]).mean() > 0.95
+    ns = int(same.sum())
+    for key in ("defl", "rot", "moment", "shear"):
+        assert rel_err(b[key][same].reshape(ns * num_cases, -1), a[key][same].reshape(ns * num_cases, -1)).max() < 1e-6, key
+    # fixed epochs: I never depends on a stop decision
+    pf = p.replace(early_stop=False, max_e=120)
+    a, b = oracle_run(pf, fixed, fn, fv, L), gpu_run(pf, fixed, fn, fv, L)
+    assert (b["epochs"] == 120).all() and np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
+    # host records: C consecutive records per beam, identical I_values (the trainers' reshape(total, n_cases, -1))
+    rollers, avail = sampling.fixed_bridge(101)
+    recs = generator.generate_samples_batched(range(6), 101, 0, 200.0, np.linspace(0, 200.0, 101), rollers, avail,
+                                              patience=10, params=p, seed=1)
+    assert len(recs) == 6 * num_cases
+    for i in range(6):
+        grp = recs[i * num_cases:(i + 1) * num_cases]
+        assert all(r["I_values"] == grp[0]["I_values"] for r in grp)
+        assert len({tuple(r["force_values"]) for r in grp}) > 1

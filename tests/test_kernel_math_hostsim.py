@@ -139,3 +139,23 @@ def test_fine_discretisation_1000_elements_three_moment():
     h = hostsim_solve(p, fixed, fn[:, 0], fv[:, 0], L, I)
     for k in ("defl", "rot", "shear", "moment"):
         assert rel_err(h[k], o80[k]).max() < 1e-9, k
+
+
+@pytest.mark.parametrize("num_cases", [2, 4, 8])
+def test_shared_inertia_load_cases_against_c_oracle(num_cases):
+    """SURVEY 8a row 15 (extension): C load cases share one I vector, energies summed in case order.  The
+    lanes kernel runs the cases on C adjacent groups that exchange M^2, V^2; the host model runs the
+    same phase functions team by team."""
+    p = BeamOptParams.for_script("MC").replace(num_cases=num_cases)
+    cases = seeded_cases(p, 24 * num_cases, seed=21)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases, num_cases)
+    a = oracle_run(p, fixed, fn, fv, L)
+    b = hostsim_run(p, fixed, fn, fv, L, solver=0)
+    assert not a["status"].any() and not b["status"].any()
+    assert np.array_equal(a["epochs"], b["epochs"])
+    assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
+    assert (a["loss"] == b["loss"]).mean() > 0.95
+    B = len(L)
+    for key in ("defl", "rot", "moment", "shear"):
+        assert rel_err(b[key].reshape(B * num_cases, -1), a[key].reshape(B * num_cases, -1)).max() < 1e-6, key
+    assert (b["defl"][:, :, -1] == 0).all()
