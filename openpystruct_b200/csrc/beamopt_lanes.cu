@@ -34,12 +34,14 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
     else asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "n"(NC * LPB) : "memory");
 }
 
-template <int EPL, int NFIX, int NC>
-__global__ void __launch_bounds__(LANES_MAX_THREADS, 1)
+// TFIX: compile-time CTA size (0 = blockDim.x).  With it every shared-memory column stride is an immediate
+// and the [slot][thread] addressing costs no integer instructions.
+template <int EPL, int NFIX, int NC, int TFIX>
+__global__ void __launch_bounds__(TFIX ? TFIX : LANES_MAX_THREADS, 1)
 beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = blockDim.x, G = T / LPB;
+    const int T = TFIX ? TFIX : (int)blockDim.x, G = T / LPB;
     const int tid = threadIdx.x, l = tid & (LPB - 1), g = tid / LPB;
     const unsigned gmask = 0xffu << (tid & 24);
     const int case_id = g % NC;                                    // load case of this group
@@ -55,10 +57,9 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     int *grp_i = reinterpret_cast<int *>(grp_d + (size_t)GROUP_DOUBLES * G);
     LaneStore ls;
     ls.ls = T;
-    ls.gq = reinterpret_cast<Pair *>(lane_d) + tid;
-    ls.mq = ls.gq + (size_t)EPL * T;
-    ls.scr = lane_d + (size_t)4 * EPL * T + tid;
-    ls.xc = reinterpret_cast<PairF *>(lane_d + (size_t)(4 * EPL + SCR_SLOTS) * T) + tid;
+    ls.mq = reinterpret_cast<Pair *>(lane_d) + tid;
+    ls.scr = lane_d + (size_t)2 * EPL * T + tid;
+    ls.xc = reinterpret_cast<PairF *>(lane_d + (size_t)(2 * EPL + SCR_SLOTS) * T) + tid;
     GroupStore gs;
     gs.gs = G;
     gs.tab = tab_d + (size_t)TAB_SLOTS * g;
@@ -71,6 +72,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 
     LaneRegs<EPL> rg;
     FlexBeam fb;
+    Pass1Consts pc = {0.0, 0.0, 0.0, 0.0};
     long long b = -1;
     bool have = false, exhausted = false;
     int t = 0, counter = 0, bad = 0;
@@ -114,9 +116,10 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                 }
                 __syncwarp(gmask);
                 bad = group_fetch(k, p.L[b], gs, fb);
+                pc = pass1_consts(fb);
                 if (!bad) {
                     lane_init<EPL>(k, n, fb, gs, ls, l, rg);
-                    lane_pass1<EPL>(rg, ls);
+                    lane_pass1<EPL>(rg, ls, pc);
                 } else {
                     lane_reset<EPL>(k, rg);
                 }
@@ -154,7 +157,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                 if (t >= k.max_epochs) done = true;
             }
             if (!done) {
-                lane_adam<EPL, true>(k, rg, ls, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
+                lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
             } else {
                 // record of the beam: fields of the last analysed inertias, then the last Adam step
                 const bool fields = (t > 0) && (bad == 0);
@@ -170,7 +173,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                         p.status[b] = bad;
                     }
                 }
-                if (t > 0) lane_adam<EPL, false>(k, rg, ls, neg_step, bc2_sqrt);
+                if (t > 0) lane_adam<EPL, false>(k, rg, ls, pc, neg_step, bc2_sqrt);
                 if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + b * n);
                 __syncwarp(gmask);
                 have = false;
@@ -222,11 +225,11 @@ int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_
     return 0;
 }
 
-template <int EPL, int NFIX, int NC>
+template <int EPL, int NFIX, int NC, int TFIX = 0>
 static cudaError_t launch_instance(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl,
                                    cudaStream_t stream)
 {
-    auto kern = beamopt_lanes_kernel<EPL, NFIX, NC>;
+    auto kern = beamopt_lanes_kernel<EPL, NFIX, NC, TFIX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<pl.blocks, pl.threads, pl.smem_bytes, stream>>>(k, B, p);
@@ -250,6 +253,8 @@ cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, con
         default: return cudaErrorInvalidValue;
         }
     }
+    if (pl.nfix == 100 && pl.threads == LANES_MAX_THREADS)
+        return launch_instance<13, 100, 1, LANES_MAX_THREADS>(k, B, p, pl, stream);      // the reference's discretisation
     if (pl.nfix == 100) return launch_instance<13, 100, 1>(k, B, p, pl, stream);
     switch (pl.epl) {
     case 4: return launch_instance<4, 0, 1>(k, B, p, pl, stream);

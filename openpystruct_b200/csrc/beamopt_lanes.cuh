@@ -8,8 +8,10 @@
 // SIMD lane l of the 8-float vectors ATen's cascade_sum works on, so torch.sum's summation order
 // (beamopt_core.cuh, torch_sum_f32) falls out of per-lane running sums plus one fixed-order combine.
 // Per element the lane keeps I, Adam's m and v, the gradient and the element's index inside its span
-// in REGISTERS; the I-independent data of the three-moment form sit in shared memory, one
-// conflict-free [slot][thread] column per lane.
+// in REGISTERS; the I-independent statics of the element ({M0, Q0} of the simply supported span) sit in
+// shared memory, one conflict-free [slot][thread] column per lane, and the flexibility weights are
+// derived from them on the fly (G = 6 M0 + 3 Le Q0 + const, g1 x1 + g2 x2 = d (G ke + g2)), which is what
+// lets 40+ beams stay resident per SM.
 //
 // Three-moment form with I-independent coefficients (beamopt_flex.cuh derives the equations).
 // With r_e = 1 / I_e, ke = index of element e inside its span, d = 1 / (elements in the span):
@@ -53,7 +55,7 @@ constexpr int GX_INTS = 6;                      // m, last, nloads, setup status
 constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + GX_DOUBLES;   // strided [slot][group] columns (+ TAB_SLOTS contiguous)
 constexpr int GROUP_INTS = FlexStore::NUM_INTS + GX_INTS;
 
-OPS_HD constexpr int lane_doubles(int epl, int nc) { return 4 * epl + SCR_SLOTS + (nc > 1 ? epl : 0); }
+OPS_HD constexpr int lane_doubles(int epl, int nc) { return 2 * epl + SCR_SLOTS + (nc > 1 ? epl : 0); }
 
 template <int EPL>
 struct LaneRegs {
@@ -72,7 +74,6 @@ struct alignas(8) PairF {                       // {M^2, V^2} of one load case, 
 };
 
 struct LaneStore {
-    Pair *gq;                                   // [EPL]: {G, Q} coefficients of the element
     Pair *mq;                                   // [EPL]: {M0, Q0} of the element
     double *scr;                                // [SCR_SLOTS]
     PairF *xc;                                  // [EPL] (multi-case kernels only): squares exchanged between the case groups
@@ -132,7 +133,7 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
     for (int kk = 0; kk < EPL; ++kk) {
         const int e = LPB * kk + l;
         int sp = DUMMY;
-        double kef = 0.0, G = 0.0, Qc = 0.0, M0 = 0.0, Q0 = 0.0;
+        double kef = 0.0, M0 = 0.0, Q0 = 0.0;
         float I0 = 1.0f;                        // padding slots: harmless inertia, never read back
         if (e < n) {
             I0 = k.I0f;
@@ -141,7 +142,6 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
                 for (int s = 1; s < m; ++s) j = (gs.fs.sup(s) <= e) ? s : j;
                 const int na = gs.fs.sup(j);
                 const double ke = (double)(e - na);
-                const double d = gs.fs.span(j + 1, FlexStore::DXI);
                 const double ra = gs.fs.span(j + 1, FlexStore::RA);
                 double Qs = fma(ke, fb.wl, ra);
                 double Ms = fma(ra, ke * fb.Le, fb.wl2h * (ke * ke));
@@ -153,11 +153,6 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
                         Ms = fma(P, (double)(e - nd) * fb.Le, Ms);
                     }
                 }
-                const double m2 = fma(Qs, fb.Le, Ms + fb.wl2h);
-                const double g1 = fma(2.0, Ms, m2) - fb.corr, g2 = fma(2.0, m2, Ms) - fb.corr;
-                const double x1 = ke * d, x2 = x1 + d;
-                G = g1 + g2;
-                Qc = fma(g1, x1, g2 * x2);
                 sp = j; kef = ke; M0 = Ms; Q0 = Qs;
             } else {
                 const double r = (double)(n - e);
@@ -180,9 +175,7 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
         }
         prev = sp;
         rg.I[kk] = I0; rg.m[kk] = 0.0f; rg.v[kk] = 0.0f; rg.g[kk] = 0.0f; rg.ke[kk] = (float)kef;
-        Pair gq; gq.x = G; gq.y = Qc;
         Pair mq; mq.x = M0; mq.y = Q0;
-        ls.gq[(long)kk * ls.ls] = gq;
         ls.mq[(long)kk * ls.ls] = mq;
     }
     if (prev != DUMMY) ends |= 1u << (EPL - 1);
@@ -211,18 +204,38 @@ struct SpanSums {
     double R0, R1, R2, G, Q;
 };
 
+// per-beam constants of the flexibility weights: with m2 = M0 + Le Q0 + w Le^2/2 (moment at the right node),
+//   G  = g1 + g2 = 6 M0 + 3 Le Q0 + (3 w Le^2/2 - 2 corr)        g2 = 3 M0 + 2 Le Q0 + (w Le^2 - corr)
+//   g1 x1 + g2 x2 = d (G ke + g2)                                  (x1 = ke d, x2 = x1 + d)
+// so PASS 1 accumulates sum r G and sum r (G ke + g2); the factor d of the span is applied in the reduction.
+struct Pass1Consts {
+    double k3Le, k2Le, cG, cg2;
+};
+OPS_HD Pass1Consts pass1_consts(const FlexBeam &fb)
+{
+    Pass1Consts c;
+    c.k3Le = 3.0 * fb.Le;
+    c.k2Le = 2.0 * fb.Le;
+    c.cG = fma(3.0, fb.wl2h, -2.0 * fb.corr);
+    c.cg2 = fma(2.0, fb.wl2h, -fb.corr);
+    return c;
+}
+
 template <int EPL>
-OPS_HD void pass1_accumulate(const LaneRegs<EPL> &rg, const LaneStore &ls, int kk, double r, SpanSums &a)
+OPS_HD void pass1_accumulate(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, int kk, double r,
+                             SpanSums &a)
 {
     const double keep = ((rg.starts >> kk) & 1u) ? 0.0 : 1.0;
     const double ke = (double)rg.ke[kk];
-    const Pair gq = ls.gq[(long)kk * ls.ls];
+    const Pair mq = ls.mq[(long)kk * ls.ls];
+    const double G = fma(6.0, mq.x, fma(pc.k3Le, mq.y, pc.cG));
+    const double g2 = fma(3.0, mq.x, fma(pc.k2Le, mq.y, pc.cg2));
     const double t = r * ke;
     a.R0 = fma(a.R0, keep, r);
     a.R1 = fma(a.R1, keep, t);
     a.R2 = fma(t, ke, a.R2 * keep);
-    a.G = fma(r, gq.x, a.G * keep);
-    a.Q = fma(r, gq.y, a.Q * keep);
+    a.G = fma(r, G, a.G * keep);
+    a.Q = fma(r, fma(G, ke, g2), a.Q * keep);
     if ((rg.ends >> kk) & 1u) {
         const int j = (int)((rg.spans >> (3 * kk)) & 7u);
         double *s = ls.scr + (long)(j * NSUM) * ls.ls;
@@ -231,11 +244,11 @@ OPS_HD void pass1_accumulate(const LaneRegs<EPL> &rg, const LaneStore &ls, int k
 }
 
 template <int EPL>
-OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls)
+OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc)
 {
     SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) pass1_accumulate<EPL>(rg, ls, kk, fm::rcp64((double)rg.I[kk]), a);
+    for (int kk = 0; kk < EPL; ++kk) pass1_accumulate<EPL>(rg, ls, pc, kk, fm::rcp64((double)rg.I[kk]), a);
 }
 
 // Group reduction of the partials and the flexibility coefficients of the span: lane j < NSPAN adds
@@ -261,8 +274,9 @@ OPS_HD void lane_reduce(int l, int m, const LaneStore &ls, const GroupStore &gs)
         gs.fs.span(l + 1, FlexStore::A) = fma(-6.0, S, fma(6.0, R[0], c));
         gs.fs.span(l + 1, FlexStore::B) = fma(3.0, S, -c);
         gs.fs.span(l + 1, FlexStore::C) = c;
-        gs.fs.span(l + 1, FlexStore::P) = R[3] - R[4];
-        gs.fs.span(l + 1, FlexStore::Q) = R[4];
+        const double q = d * R[4];
+        gs.fs.span(l + 1, FlexStore::P) = R[3] - q;
+        gs.fs.span(l + 1, FlexStore::Q) = q;
     }
 }
 
@@ -383,79 +397,90 @@ OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const Lan
     float aI[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ad[4] = {0.0f, 0.0f, 0.0f, 0.0f}, aq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float tI = 0.0f, td = 0.0f, tq = 0.0f;
     const PairF *x0 = ls.xc - (long)case_id * LPB;             // this lane's column in the team's case-0 group
+    // one operation per stage across the batch (OPS_B: "for every live slot i of the batch"); the fast-path
+    // sequences of fastmath.cuh are written out step by step so that consecutive instructions are independent
+#define OPS_B _Pragma("unroll") for (int i = 0; i < NB; ++i) if (k0 + i < EPL)
 #pragma unroll
     for (int k0 = 0; k0 < EPL; k0 += NB) {
-        double Mc[NB], Qv[NB];
-        float c[NB], h[NB], b[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB];
+        float I[NB], c[NB], h[NB], b[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB];
+        float t0[NB], t1[NB], t2[NB];
+        OPS_B I[i] = rg.I[k0 + i];
         if (NC == 1) {
+            Pair lo[NB], mq[NB];
+            double tq2[NB], ke[NB], Mc[NB], Qv[NB];
+            OPS_B {
+                const int j = (int)((rg.spans >> (3 * (k0 + i))) & 7u);
+                lo[i] = reinterpret_cast<const Pair *>(gs.tab)[j];
+                tq2[i] = gs.tab[TAB_T2 + j];
+                mq[i] = ls.mq[(long)(k0 + i) * ls.ls];
+                ke[i] = (double)rg.ke[k0 + i];
+            }
+            OPS_B { Mc[i] = mq[i].x + lo[i].x; Qv[i] = mq[i].y + tq2[i]; }
+            OPS_B Mc[i] = fma(lo[i].y, ke[i], Mc[i]);
+            OPS_B { c[i] = (float)Mc[i]; h[i] = (float)Qv[i]; }
+            OPS_B { c[i] = c[i] * c[i]; h[i] = h[i] * h[i]; }
+        } else {
+            OPS_B {
+                PairF x = x0[(long)(k0 + i) * ls.ls];
+                c[i] = x.c; h[i] = x.h;
 #pragma unroll
-            for (int i = 0; i < NB; ++i)
-                if (k0 + i < EPL) element_forces<EPL>(rg, ls, gs, k0 + i, Mc[i], Qv[i]);
+                for (int cc = 1; cc < NC; ++cc) {
+                    x = x0[(long)(k0 + i) * ls.ls + cc * LPB];
+                    c[i] += x.c; h[i] += x.h;
+                }
+            }
         }
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (k0 + i < EPL) {
-                const float I = rg.I[k0 + i];
-                if (NC == 1) {
-                    const float Mf = (float)Mc[i], Vf = (float)Qv[i];
-                    c[i] = Mf * Mf;
-                    h[i] = Vf * Vf;
-                } else {
-                    PairF x = x0[(long)(k0 + i) * ls.ls];
-                    c[i] = x.c; h[i] = x.h;
-#pragma unroll
-                    for (int cc = 1; cc < NC; ++cc) {
-                        x = x0[(long)(k0 + i) * ls.ls + cc * LPB];
-                        c[i] += x.c; h[i] += x.h;
-                    }
-                }
-                b[i] = k.E2 * I + k.epsf;
-                y[i] = fm::rsq_a(I);
-                rb[i] = fm::rcp_a(b[i]);
+        OPS_B { b[i] = k.E2 * I[i]; y[i] = fm::rsq_a(I[i]); }
+        OPS_B b[i] = b[i] + k.epsf;
+        // rb = refined 1 / b ; s = sqrt(I)
+        OPS_B { rb[i] = fm::rcp_a(b[i]); t0[i] = I[i] * y[i]; y[i] = y[i] * 0.5f; }
+#if defined(__CUDA_ARCH__)
+        OPS_B { t1[i] = fmaf(-b[i], rb[i], 1.0f); t2[i] = fmaf(-t0[i], t0[i], I[i]); }
+        OPS_B { rb[i] = fmaf(rb[i], t1[i], rb[i]); s[i] = fmaf(t2[i], y[i], t0[i]); }
+        // d = c / b ; gg = Gf (kf s) ; rs = 1 / s
+        OPS_B { t0[i] = c[i] * rb[i]; gg[i] = k.kf * s[i]; rs[i] = fm::rcp_a(s[i]); }
+        OPS_B { t1[i] = fmaf(-b[i], t0[i], c[i]); gg[i] = k.Gf * gg[i]; t2[i] = fmaf(-s[i], rs[i], 1.0f); }
+        OPS_B { d[i] = fmaf(rb[i], t1[i], t0[i]); rgg[i] = fm::rcp_a(gg[i]); rs[i] = fmaf(rs[i], t2[i], rs[i]); }
+        // db = d / b ; rgg = refined 1 / gg ; rs = RN(1 / s)
+        OPS_B { t0[i] = d[i] * rb[i]; t1[i] = fmaf(-gg[i], rgg[i], 1.0f); t2[i] = fmaf(-s[i], rs[i], 1.0f); }
+        OPS_B { db[i] = fmaf(-b[i], t0[i], d[i]); rgg[i] = fmaf(rgg[i], t1[i], rgg[i]); rs[i] = fmaf(rs[i], t2[i], rs[i]); }
+        OPS_B { db[i] = fmaf(rb[i], db[i], t0[i]); t1[i] = h[i] * rgg[i]; rs[i] = 0.5f * rs[i]; }
+        // q = h / gg ; bending branch gb = ((-am) db) E2
+        OPS_B { db[i] = (-k.am) * db[i]; t2[i] = fmaf(-gg[i], t1[i], h[i]); }
+        OPS_B { db[i] = db[i] * k.E2; q[i] = fmaf(rgg[i], t2[i], t1[i]); }
+        // qg = q / gg
+        OPS_B t0[i] = q[i] * rgg[i];
+        OPS_B t1[i] = fmaf(-gg[i], t0[i], q[i]);
+        OPS_B qg[i] = fmaf(rgg[i], t1[i], t0[i]);
+#else
+        OPS_B {
+            s[i] = sqrtf(I[i]);
+            d[i] = c[i] / b[i];
+            db[i] = ((-k.am) * (d[i] / b[i])) * k.E2;
+            gg[i] = k.Gf * (k.kf * s[i]);
+            q[i] = h[i] / gg[i];
+            qg[i] = q[i] / gg[i];
+            rs[i] = 0.5f * (1.0f / s[i]);
+        }
+        (void)rb; (void)rgg; (void)t0; (void)t1; (void)t2; (void)y;
+#endif
+        // shear branch gs = ((((-as) qg) Gf) kf) (0.5 / s) ; g = (1 + gs) + gb
+        OPS_B qg[i] = (-k.as_) * qg[i];
+        OPS_B qg[i] = qg[i] * k.Gf;
+        OPS_B qg[i] = qg[i] * k.kf;
+        OPS_B qg[i] = qg[i] * rs[i];
+        OPS_B qg[i] = 1.0f + qg[i];
+        OPS_B rg.g[k0 + i] = qg[i] + db[i];
+        OPS_B {
+            const int kk = k0 + i;
+            if (kk < sh.blk) {
+                aI[kk & 3] += I[i]; ad[kk & 3] += d[i]; aq[kk & 3] += q[i];
+            } else if (kk < sh.vec) {
+                aI[0] += I[i]; ad[0] += d[i]; aq[0] += q[i];
+            } else if (kk == sh.vec && l < sh.ntail) {
+                tI = I[i]; td = d[i]; tq = q[i];
             }
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (k0 + i < EPL) {
-                rb[i] = fm::rcp_n(b[i], rb[i]);
-                s[i] = fm::sqrt_n(rg.I[k0 + i], y[i]);
-                gg[i] = k.Gf * (k.kf * s[i]);
-                rgg[i] = fm::rcp_a(gg[i]);
-                rs[i] = fm::rcp_a(s[i]);
-            }
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (k0 + i < EPL) {
-                d[i] = fm::div_r(c[i], b[i], rb[i]);
-                rgg[i] = fm::rcp_n(gg[i], rgg[i]);
-                rs[i] = fm::rcp_n(s[i], rs[i]);
-            }
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (k0 + i < EPL) {
-                db[i] = fm::div_r(d[i], b[i], rb[i]);
-                q[i] = fm::div_r(h[i], gg[i], rgg[i]);
-                rs[i] = fm::rcp_fin(s[i], rs[i]);                    // 1 / sqrt(I)
-            }
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (k0 + i < EPL) {
-                qg[i] = fm::div_r(q[i], gg[i], rgg[i]);
-                db[i] = ((-k.am) * db[i]) * k.E2;                    // bending branch of the gradient
-            }
-#pragma unroll
-        for (int i = 0; i < NB; ++i)
-            if (k0 + i < EPL) {
-                const int kk = k0 + i;
-                const float gs_ = ((((-k.as_) * qg[i]) * k.Gf) * k.kf) * (0.5f * rs[i]);
-                rg.g[kk] = (1.0f + gs_) + db[i];
-                if (kk < sh.blk) {
-                    aI[kk & 3] += rg.I[kk]; ad[kk & 3] += d[i]; aq[kk & 3] += q[i];
-                } else if (kk < sh.vec) {
-                    aI[0] += rg.I[kk]; ad[0] += d[i]; aq[0] += q[i];
-                } else if (kk == sh.vec && l < sh.ntail) {
-                    tI = rg.I[kk]; td = d[i]; tq = q[i];
-                }
-            }
+        }
     }
     float *st = reinterpret_cast<float *>(ls.scr + (long)SCR_STAGE * ls.ls);
     const long fs_ = 2 * ls.ls;                 // float stride between slots
@@ -488,49 +513,66 @@ OPS_HD float group_loss(const BeamConsts &k, int n, const LaneStore &ls, int l)
 // every epoch so far -- tested once per lane and epoch, with the generic operators as the (cold)
 // alternative.
 template <int EPL, bool PASS1>
-OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &ls, float neg_step, float bc2_sqrt)
+OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc,
+                      float neg_step, float bc2_sqrt)
 {
     bool rare = false;
-#pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) {
-        const float g = rg.g[kk];
-        rg.m[kk] = fmaf(k.w1, g - rg.m[kk], rg.m[kk]);
-        rg.v[kk] = fmaf(k.omb2f * g, g, rg.v[kk] * k.b2f);
-        rare = rare || !(rg.v[kk] >= fm::SQRT_F_MIN);
+    {
+        float t0[EPL], t1[EPL];
+#define OPS_A _Pragma("unroll") for (int kk = 0; kk < EPL; ++kk)
+        OPS_A { t0[kk] = rg.g[kk] - rg.m[kk]; t1[kk] = k.omb2f * rg.g[kk]; rg.v[kk] = rg.v[kk] * k.b2f; }
+        OPS_A { rg.m[kk] = fmaf(k.w1, t0[kk], rg.m[kk]); rg.v[kk] = fmaf(t1[kk], rg.g[kk], rg.v[kk]); }
+        OPS_A rare = rare || !(rg.v[kk] >= fm::SQRT_F_MIN);
+#undef OPS_A
     }
     if (!rare) {
         const float rbc = fm::rcp_r(bc2_sqrt);
         SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int k0 = 0; k0 < EPL; k0 += NB) {
-            float y[NB], den[NB], rd[NB];
+            float y[NB], den[NB], rd[NB], t0[NB], t1[NB], num[NB];
             double Id[NB], r[NB];
-#pragma unroll
-            for (int i = 0; i < NB; ++i)
-                if (k0 + i < EPL) y[i] = fm::rsq_a(rg.v[k0 + i]);
-#pragma unroll
-            for (int i = 0; i < NB; ++i)
-                if (k0 + i < EPL) {
-                    den[i] = fm::div_r(fm::sqrt_n(rg.v[k0 + i], y[i]), bc2_sqrt, rbc) + k.adam_epsf;
-                    rd[i] = fm::rcp_a(den[i]);
-                }
-#pragma unroll
-            for (int i = 0; i < NB; ++i)
-                if (k0 + i < EPL) {
-                    const float x = rg.I[k0 + i] + fm::div_r(neg_step * rg.m[k0 + i], den[i], fm::rcp_n(den[i], rd[i]));
-                    rg.I[k0 + i] = x < k.clampf ? k.clampf : x;
-                    if (PASS1) {
-                        Id[i] = (double)rg.I[k0 + i];
-                        r[i] = fm::rcp64_a(Id[i]);
-                    }
-                }
+#if defined(__CUDA_ARCH__)
+            // sqrt(v) / bc2_sqrt + eps
+            OPS_B y[i] = fm::rsq_a(rg.v[k0 + i]);
+            OPS_B { t0[i] = rg.v[k0 + i] * y[i]; y[i] = y[i] * 0.5f; num[i] = neg_step * rg.m[k0 + i]; }
+            OPS_B t1[i] = fmaf(-t0[i], t0[i], rg.v[k0 + i]);
+            OPS_B t0[i] = fmaf(t1[i], y[i], t0[i]);                  // sqrt(v)
+            OPS_B t1[i] = t0[i] * rbc;
+            OPS_B den[i] = fmaf(-bc2_sqrt, t1[i], t0[i]);
+            OPS_B den[i] = fmaf(rbc, den[i], t1[i]);
+            OPS_B den[i] = den[i] + k.adam_epsf;
+            // I + (neg_step m) / denom, clamp
+            OPS_B rd[i] = fm::rcp_a(den[i]);
+            OPS_B t0[i] = fmaf(-den[i], rd[i], 1.0f);
+            OPS_B rd[i] = fmaf(rd[i], t0[i], rd[i]);
+            OPS_B t0[i] = num[i] * rd[i];
+            OPS_B t1[i] = fmaf(-den[i], t0[i], num[i]);
+            OPS_B t0[i] = fmaf(rd[i], t1[i], t0[i]);
+            OPS_B t0[i] = rg.I[k0 + i] + t0[i];
+            OPS_B rg.I[k0 + i] = t0[i] < k.clampf ? k.clampf : t0[i];
             if (PASS1) {
-#pragma unroll
-                for (int i = 0; i < NB; ++i)
-                    if (k0 + i < EPL) r[i] = fm::rcp64_n(Id[i], r[i]);
-#pragma unroll
-                for (int i = 0; i < NB; ++i)
-                    if (k0 + i < EPL) pass1_accumulate<EPL>(rg, ls, k0 + i, r[i], a);
+                double e[NB];
+                OPS_B Id[i] = (double)rg.I[k0 + i];
+                OPS_B r[i] = fm::rcp64_a(Id[i]);
+                OPS_B e[i] = fma(-Id[i], r[i], 1.0);
+                OPS_B e[i] = fma(e[i], e[i], e[i]);
+                OPS_B r[i] = fma(r[i], e[i], r[i]);
+                OPS_B e[i] = fma(-Id[i], r[i], 1.0);
+                OPS_B r[i] = fma(r[i], e[i], r[i]);
+            }
+#else
+            OPS_B {
+                den[i] = sqrtf(rg.v[k0 + i]) / bc2_sqrt + k.adam_epsf;
+                const float x = rg.I[k0 + i] + (neg_step * rg.m[k0 + i]) / den[i];
+                rg.I[k0 + i] = x < k.clampf ? k.clampf : x;
+                Id[i] = (double)rg.I[k0 + i];
+                r[i] = 1.0 / Id[i];
+            }
+            (void)y; (void)rd; (void)t0; (void)t1; (void)num; (void)rbc;
+#endif
+            if (PASS1) {
+                OPS_B pass1_accumulate<EPL>(rg, ls, pc, k0 + i, r[i], a);
             }
         }
     } else {
@@ -540,9 +582,10 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &l
             const float x = rg.I[kk] + (neg_step * rg.m[kk]) / denom;
             rg.I[kk] = x < k.clampf ? k.clampf : x;
         }
-        if (PASS1) lane_pass1<EPL>(rg, ls);
+        if (PASS1) lane_pass1<EPL>(rg, ls, pc);
     }
 }
+#undef OPS_B
 
 // ---------------------------------------------------------------------------------------------
 // once per beam: the record (SingleCore:221-249).  M, V, u, theta belong to the LAST ANALYSED

@@ -226,7 +226,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
     using namespace ops::lanes;
     const int n = k.n, nn = k.nn;
     constexpr int TL = NC * LPB;                       // lanes of a team; column index = case * 8 + lane
-    std::vector<Pair> lane_p((size_t)2 * EPL * TL);
+    std::vector<Pair> lane_p((size_t)EPL * TL);
     std::vector<double> lane_s((size_t)SCR_SLOTS * TL), grp_d((size_t)GROUP_DOUBLES * NC);
     std::vector<PairF> lane_x((size_t)EPL * TL);
     std::vector<Pair> tab_p((size_t)TAB_SLOTS / 2 * NC);
@@ -237,8 +237,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
         for (int l = 0; l < LPB; ++l) {
             const int col = c * LPB + l;
             ls[c][l].ls = TL;
-            ls[c][l].gq = lane_p.data() + col;
-            ls[c][l].mq = ls[c][l].gq + (size_t)EPL * TL;
+            ls[c][l].mq = lane_p.data() + col;
             ls[c][l].scr = lane_s.data() + col;
             ls[c][l].xc = lane_x.data() + col;
         }
@@ -267,7 +266,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             group_table_init(gs[c]);
             bad = group_fetch(k, L[b], gs[c], fb[c]);
             for (int l = 0; l < LPB; ++l) {
-                if (!bad) { lane_init<EPL>(k, n, fb[c], gs[c], ls[c][l], l, rg[c][l]); lane_pass1<EPL>(rg[c][l], ls[c][l]); }
+                if (!bad) { lane_init<EPL>(k, n, fb[c], gs[c], ls[c][l], l, rg[c][l]); lane_pass1<EPL>(rg[c][l], ls[c][l], pass1_consts(fb[c])); }
                 else lane_reset<EPL>(k, rg[c][l]);
             }
         }
@@ -301,7 +300,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             if (t >= k.max_epochs) done = true;
             if (!done)
                 for (int c = 0; c < NC; ++c)
-                    for (int l = 0; l < LPB; ++l) lane_adam<EPL, true>(k, rg[c][l], ls[c][l], neg_step, bc2_sqrt);
+                    for (int l = 0; l < LPB; ++l) lane_adam<EPL, true>(k, rg[c][l], ls[c][l], pass1_consts(fb[c]), neg_step, bc2_sqrt);
         }
         const bool fields = (t > 0) && (bad == 0);
         for (int c = 0; c < NC; ++c) {
@@ -310,7 +309,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
                 lane_emit_forces<EPL>(n, rg[c][l], ls[c][l], gs[c], l, fields, shear + bc * n, moment + bc * n);
             group_emit_displacements(k, fb[c], ls[c][0], gs[c], fields, defl + bc * nn, rot + bc * nn);
             for (int l = 0; l < LPB; ++l) {
-                if (t > 0) lane_adam<EPL, false>(k, rg[c][l], ls[c][l], neg_step, bc2_sqrt);
+                if (t > 0) lane_adam<EPL, false>(k, rg[c][l], ls[c][l], pass1_consts(fb[c]), neg_step, bc2_sqrt);
                 if (c == 0) lane_emit_inertias<EPL>(n, rg[c][l], l, I_values + b * n);
             }
         }
