@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -284,8 +285,8 @@ __device__ __forceinline__ float rand_float(unsigned long long &s, int elo, int 
 __global__ void fastmath_selftest_kernel(int per_thread, unsigned long long seed, unsigned long long *out)
 {
     unsigned long long s = seed + 0x9E3779B97F4A7C15ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
-    unsigned long long bad_div = 0, bad_sqrt = 0, bad_rcp = 0;
-    double worst = 0.0;
+    unsigned long long bad_div = 0, bad_sqrt = 0, bad_rcp = 0, bad_rsq = 0;
+    double worst = 0.0, worst_seed = 0.0;
     for (int i = 0; i < per_thread; ++i) {
         // division: b in [2^-60, 2^60], a zero or in [2^-60, 2^60]  (quotient within [2^-120, 2^120])
         const float b = rand_float(s, 67, 187);
@@ -305,31 +306,38 @@ __global__ void fastmath_selftest_kernel(int per_thread, unsigned long long seed
         const double xd = (double)rand_float(s, 87, 167);
         const double e = fabs(fm::rcp64(xd) * xd - 1.0);
         worst = e > worst ? e : worst;
+        const double e0 = fabs(fm::rcp64_a(xd) * xd - 1.0);          // the bare MUFU.RCP64H seed
+        worst_seed = e0 > worst_seed ? e0 : worst_seed;
     }
     atomicAdd(out + 0, bad_div);
     atomicAdd(out + 1, bad_sqrt);
     atomicAdd(out + 2, bad_rcp);
     atomicMax(out + 3, (unsigned long long)__double_as_longlong(worst));
+    atomicAdd(out + 4, bad_rsq);
+    atomicMax(out + 5, (unsigned long long)__double_as_longlong(worst_seed));
 }
 
 cudaError_t fastmath_selftest(long long samples, unsigned long long *host_out4, double *worst_rcp64, cudaStream_t stream)
 {
     unsigned long long *d = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d, 32);
+    cudaError_t e = cudaMalloc((void **)&d, 64);
     if (e != cudaSuccess) return e;
-    cudaMemsetAsync(d, 0, 32, stream);
+    cudaMemsetAsync(d, 0, 64, stream);
     const int threads = 256, blocks = 592;
     int per_thread = (int)(samples / ((long long)threads * blocks)) + 1;
     fastmath_selftest_kernel<<<blocks, threads, 0, stream>>>(per_thread, 0x1234567ULL, d);
     e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out4, d, 32, cudaMemcpyDeviceToHost, stream);
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(d);
     if (e != cudaSuccess) return e;
-    long long bits = (long long)host_out4[3];
-    double w;
-    memcpy(&w, &bits, 8);
+    double w, w0;
+    memcpy(&w, &h[3], 8);
+    memcpy(&w0, &h[5], 8);
     *worst_rcp64 = w;
+    if (getenv("OPS_SELFTEST_VERBOSE")) printf("rcp64 seed max rel err %.3e, refined %.3e\n", w0, w);
+    host_out4[0] = h[0]; host_out4[1] = h[1]; host_out4[2] = h[2] + h[4];     // reciprocal mismatches incl. 1/sqrt
     host_out4[3] = (unsigned long long)per_thread * threads * blocks;
     return cudaSuccess;
 }

@@ -555,10 +555,8 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &l
                 double e[NB];
                 OPS_B Id[i] = (double)rg.I[k0 + i];
                 OPS_B r[i] = fm::rcp64_a(Id[i]);
-                OPS_B e[i] = fma(-Id[i], r[i], 1.0);
+                OPS_B e[i] = fma(-Id[i], r[i], 1.0);           // rcp64_n, stage by stage
                 OPS_B e[i] = fma(e[i], e[i], e[i]);
-                OPS_B r[i] = fma(r[i], e[i], r[i]);
-                OPS_B e[i] = fma(-Id[i], r[i], 1.0);
                 OPS_B r[i] = fma(r[i], e[i], r[i]);
             }
 #else

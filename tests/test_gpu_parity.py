@@ -55,7 +55,7 @@ def test_branch_free_div_sqrt_are_ieee():
     r = _cabi.fastmath_selftest(1 << 27)
     assert r["samples"] >= 1 << 27
     assert (r["div"], r["sqrt"], r["rcp"]) == (0, 0, 0), r
-    assert r["rcp64_max_rel_err"] < 4.5e-16, r
+    assert r["rcp64_max_rel_err"] < 6.7e-16, r            # <= 3 ulp of 1/x
 
 
 @pytest.mark.parametrize("solver", SOLVERS)
