@@ -71,6 +71,14 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     gs.gi = gs.fs.si + (size_t)FlexStore::NUM_INTS * G;
     int *team_gi = gs.gi - case_id;                                // the case-0 group's ints
 
+    // Work distribution: beam b belongs to CTA b mod gridDim.x, and the groups of a CTA take the CTA's
+    // beams in order from a counter in shared memory.  Every SM gets the same number of beams (+-1), so
+    // the last, partially filled round runs with few groups on EVERY SM (short iterations) instead of
+    // full on some SMs and empty on others; ragged stopping is still absorbed inside the CTA.
+    __shared__ unsigned int cta_next;
+    if (tid == 0) cta_next = 0;
+    __syncthreads();
+
     LaneRegs<EPL> rg;
     FlexBeam fb;
     Pass1Consts pc = {0.0, 0.0, 0.0, 0.0};
@@ -84,11 +92,11 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
         if (!have && !exhausted) {
             long long nb = 0;
             if (NC == 1) {
-                if (l == 0) nb = (long long)atomicAdd(p.counter, 1ULL);
+                if (l == 0) nb = (long long)blockIdx.x + (long long)gridDim.x * atomicAdd(&cta_next, 1u);
                 nb = __shfl_sync(gmask, nb, 0, LPB);
             } else {
                 if (case_id == 0 && l == 0) {
-                    nb = (long long)atomicAdd(p.counter, 1ULL);
+                    nb = (long long)blockIdx.x + (long long)gridDim.x * atomicAdd(&cta_next, 1u);
                     team_gi[4 * G] = (int)(nb & 0xffffffffLL);
                     team_gi[5 * G] = (int)(nb >> 32);
                 }
