@@ -194,6 +194,15 @@ void ops_beamopt_session_destroy(OpsBeamOptSession *s);
 int ops_fp64_peak_probe(int iters, double *tflops, float *elapsed_ms, void *cuda_stream);
 
 /*
+ * Diagnostic (no reference counterpart): sustained issue rate of one instruction class, in warp
+ * instructions per clock per SM at the device's maximum clock (8 independent chains per thread,
+ * 1024 threads per SM).  op: 0 DFMA, 1 FFMA, 2 FMUL, 3 FADD, 4 MUFU.RCP, 5 F2F (f32<->f64), 6 IMAD,
+ * 7 LOP3, 8 FFMA with immediate operands.  Used by profiles/ to put the kernel's instruction mix
+ * against the pipes that execute it.
+ */
+int ops_pipe_probe(int op, int iters, double *warp_inst_per_clk_per_sm, void *cuda_stream);
+
+/*
  * Diagnostic (no reference counterpart): checks the branch-free fp32 division / square-root
  * sequences of the production kernel (csrc/fastmath.cuh) against the compiler's IEEE `/` and sqrtf
  * on `samples` random operands inside the ranges the kernel guarantees.  mismatches3 receives the

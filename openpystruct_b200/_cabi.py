@@ -15,7 +15,7 @@ _lib = None
 EXPORTS = (
     "ops_beamopt_version", "ops_device_count", "ops_set_device", "ops_beamopt_fill_schedule",
     "ops_beamopt_workspace_bytes", "ops_beamopt_launch", "ops_beamsolve_launch", "ops_beamopt_run_host",
-    "ops_fp64_peak_probe", "ops_fastmath_selftest",
+    "ops_fp64_peak_probe", "ops_fastmath_selftest", "ops_pipe_probe",
     "ops_beamopt_session_create", "ops_beamopt_session_arrays", "ops_beamopt_session_run",
     "ops_beamopt_session_destroy",
 )
@@ -77,6 +77,7 @@ def lib():
         L.ops_fp64_peak_probe.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p]
         L.ops_fastmath_selftest.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                             C.POINTER(C.c_double), C.c_void_p]
+        L.ops_pipe_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
         L.ops_beamopt_session_create.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64, C.c_int,
                                                  C.POINTER(C.c_void_p)]
         L.ops_beamopt_session_arrays.argtypes = [C.c_void_p, C.POINTER(OpsBeamOptHostArrays)]
@@ -224,3 +225,16 @@ class Session:
             self.close()
         except Exception:
             pass
+
+
+PIPE_PROBE_OPS = ("DFMA", "FFMA", "FMUL", "FADD", "MUFU.RCP", "F2F f32<->f64", "IMAD", "LOP3", "FFMA imm")
+
+
+def pipe_probe(iters: int = 1 << 14) -> dict:
+    """Sustained warp instructions per clock per SM of each instruction class (diagnostic)."""
+    out = {}
+    for op, name in enumerate(PIPE_PROBE_OPS):
+        r = C.c_double(0.0)
+        check(lib().ops_pipe_probe(op, iters, C.byref(r), 0), "ops_pipe_probe")
+        out[name] = float(r.value)
+    return out

@@ -498,6 +498,40 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double seed,
     if (s == 12345.678) sink[0] = s;     // never true; keeps the chains alive
 }
 
+// Issue-rate probe of one instruction class: 8 independent chains per thread, 1024 threads per SM.
+//   0 DFMA   1 FFMA (3 register operands)   2 FMUL   3 FADD   4 MUFU.RCP   5 F2F.F64.F32 + F2F.F32.F64
+//   6 IMAD   7 LOP3   8 FFMA with an immediate operand
+template <int OP>
+__global__ void __launch_bounds__(256) pipe_probe_kernel(int iters, float seed, float *sink)
+{
+    float a[8];
+    double d[8];
+    int n[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = seed + threadIdx.x + j; d[j] = a[j]; n[j] = (int)a[j]; }
+    const float m = 0.9999f + seed * 1e-9f, c = 1e-7f + seed * 1e-12f;
+    const double md = m, cd = c;
+    const int mi = 3 + (int)seed;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (OP == 0) d[j] = fma(d[j], md, cd);
+            if (OP == 1) a[j] = fmaf(a[j], m, c);
+            if (OP == 2) a[j] = a[j] * m;
+            if (OP == 3) a[j] = a[j] + c;
+            if (OP == 4) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+            if (OP == 5) { d[j] = (double)a[j]; asm volatile("" : "+d"(d[j])); a[j] = (float)d[j]; asm volatile("" : "+f"(a[j])); }
+            if (OP == 6) n[j] = n[j] * mi + i;
+            if (OP == 7) n[j] = (n[j] ^ mi) & (i | 0x55);
+            if (OP == 8) a[j] = fmaf(a[j], 0.9999f, 1e-7f);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j] + (float)d[j] + (float)n[j];
+    if (s == 12345.678f) sink[0] = s;
+}
+
 }  // namespace ops
 
 using namespace ops;
@@ -706,6 +740,39 @@ int ops_fastmath_selftest(int64_t samples, int64_t *mismatches3, int64_t *sample
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     mismatches3[0] = (int64_t)out[0]; mismatches3[1] = (int64_t)out[1]; mismatches3[2] = (int64_t)out[2];
     *samples_run = (int64_t)out[3];
+    return 0;
+}
+
+int ops_pipe_probe(int op, int iters, double *warp_inst_per_clk_per_sm, void *cuda_stream)
+{
+    if (iters <= 0 || !warp_inst_per_clk_per_sm || op < 0 || op > 8) return OPS_E_BADARG;
+    int dev = 0, sms = 0, khz = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    float *sink = nullptr;
+    e = cudaMalloc((void **)&sink, 4);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    const int blocks = sms * 4, threads = 256;
+    void (*kerns[9])(int, float, float *) = {pipe_probe_kernel<0>, pipe_probe_kernel<1>, pipe_probe_kernel<2>,
+                                             pipe_probe_kernel<3>, pipe_probe_kernel<4>, pipe_probe_kernel<5>,
+                                             pipe_probe_kernel<6>, pipe_probe_kernel<7>, pipe_probe_kernel<8>};
+    kerns[op]<<<blocks, threads, 0, stream>>>(iters / 8 + 1, 1.0f, sink);
+    cudaEventRecord(ev0, stream);
+    kerns[op]<<<blocks, threads, 0, stream>>>(iters, 1.0f, sink);
+    cudaEventRecord(ev1, stream);
+    e = cudaStreamSynchronize(stream);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaFree(sink);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    const double per_op = (op == 5) ? 2.0 : 1.0;
+    const double warp_inst = per_op * 8.0 * (double)iters * blocks * threads / 32.0;
+    *warp_inst_per_clk_per_sm = warp_inst / ((double)ms * 1e-3 * (double)khz * 1e3) / sms;
     return 0;
 }
 
