@@ -171,6 +171,24 @@ def generate_dataset(config: Optional[GeneratorConfig] = None, num_samples: Opti
     return training_data
 
 
+def generate_columnar(config: Optional[GeneratorConfig] = None, num_samples: Optional[int] = None,
+                      seed: Optional[int] = 0, device="cuda") -> dict:
+    """``generate_dataset`` without the per-record Python objects: one array per key of the record
+    (``dataset.columnar_from_run``), ready for ``dataset.save_npz`` / ``save_json``.  One launch."""
+    from . import dataset as _dataset
+    cfg = config or GeneratorConfig()
+    p = cfg.params
+    N = cfg.num_samples if num_samples is None else num_samples
+    rollers, available = sampling.fixed_bridge(p.num_nodes, cfg.roller_nodes)
+    rng = random.Random(seed) if seed is not None else random
+    cases = [sampling.sample_case(p.num_nodes, cfg.random_bridge, cfg.L_max, rollers, available, L_max=cfg.L_max,
+                                  L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max, M_forces_max=cfg.M_forces_max,
+                                  max_force=cfg.max_force, min_force=cfg.min_force, rng=rng)
+             for _ in range(N * p.num_cases)]
+    out = optimise_cases(p, cases, device)
+    return _dataset.columnar_from_run(p, cases, out)
+
+
 def save_training_data(training_data: dict, path: str = "training_data_PINN_mini.json") -> None:
     """json.dump of the dict-of-lists, the file the trainers json.load (SingleCore:263-264, PINN:192-206)."""
     def default(o):

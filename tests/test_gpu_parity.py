@@ -337,3 +337,22 @@ def test_shared_inertia_load_cases(num_cases):
         grp = recs[i * num_cases:(i + 1) * num_cases]
         assert all(r["I_values"] == grp[0]["I_values"] for r in grp)
         assert len({tuple(r["force_values"]) for r in grp}) > 1
+
+
+def test_columnar_dataset_and_trainer_preprocessing_on_device(tmp_path):
+    """one launch -> columnar arrays -> JSON / npz -> the trainers' dict; the
+    trainers' pre-processing block on the GPU."""
+    from openpystruct_b200 import dataset
+    cfg = generator.GeneratorConfig.multi_core()
+    col = generator.generate_columnar(cfg, num_samples=96, seed=3)
+    data = generator.generate_dataset(cfg, num_samples=96, seed=3)
+    got = dataset.to_training_data(col)
+    import json as _json
+    for k in generator.TRAINING_DATA_KEYS:
+        assert _json.loads(_json.dumps(got[k])) == _json.loads(_json.dumps(data[k], default=float)), k
+    dataset.save_npz(col, tmp_path / "d.npz")
+    back = dataset.load_training_data(str(tmp_path / "d.npz"))
+    assert back["I_values"] == got["I_values"] and back["deflections"] == got["deflections"]
+    pre = dataset.trainer_preprocess(back, n_cases=4, c=0.5, seed=0, device="cuda")
+    assert pre["X_train"].is_cuda and pre["X_train"].shape[0] == int(0.8 * 24)
+    assert pre["Y_train"].shape[1] == 100 + 101 + 101 and torch.isfinite(pre["Y_train"]).all()
