@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(int iters, float seed, 
             if (OP == 1) a[j] = fmaf(a[j], m, c);
             if (OP == 2) a[j] = a[j] * m;
             if (OP == 3) a[j] = a[j] + c;
-            if (OP == 4) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+            if (OP == 4) { float t_; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(t_) : "f"(a[j])); a[j] = t_; }
             if (OP == 5) { d[j] = (double)a[j]; asm volatile("" : "+d"(d[j])); a[j] = (float)d[j]; asm volatile("" : "+f"(a[j])); }
             if (OP == 6) n[j] = n[j] * mi + i;
             if (OP == 7) n[j] = (n[j] ^ mi) & (i | 0x55);
