@@ -103,7 +103,8 @@ def _check_inputs(p, fixed_uy, force_nodes, force_vals, L):
     return B, fixed_uy, force_nodes, force_vals, L
 
 
-def beamopt(p: Params, fixed_uy, force_nodes, force_vals, L) -> dict:
+def beamopt(p: Params, fixed_uy, force_nodes, force_vals, L, fe_precision: int = 0) -> dict:
+    """fe_precision 0 = FP64 dpbsv restatement (the reference's arithmetic), 1 = 80-bit FE solve."""
     L = np.asarray(L, np.float64).reshape(-1)
     B, fixed_uy, force_nodes, force_vals, L = _check_inputs(p, fixed_uy, force_nodes, force_vals, L)
     nn, Cc = p.num_nodes, p.num_cases
@@ -113,12 +114,12 @@ def beamopt(p: Params, fixed_uy, force_nodes, force_vals, L) -> dict:
         "shear": np.zeros((B, Cc, n), np.float32), "moment": np.zeros((B, Cc, n), np.float32),
         "epochs": np.zeros(B, np.int32), "loss": np.zeros(B, np.float32), "status": np.zeros(B, np.int32),
     }
-    rc = lib().oracle_beamopt(C.byref(p), C.c_int64(B), _p(fixed_uy, C.c_uint8), _p(force_nodes, C.c_int32),
+    rc = lib().oracle_beamopt_prec(C.byref(p), C.c_int64(B), _p(fixed_uy, C.c_uint8), _p(force_nodes, C.c_int32),
                               _p(force_vals, C.c_double), _p(L, C.c_double), _p(out["I"], C.c_float),
                               _p(out["defl"], C.c_double), _p(out["rot"], C.c_double),
                               _p(out["shear"], C.c_float), _p(out["moment"], C.c_float),
                               _p(out["epochs"], C.c_int32), _p(out["loss"], C.c_float),
-                              _p(out["status"], C.c_int32))
+                              _p(out["status"], C.c_int32), C.c_int(fe_precision))
     if rc != 0:
         raise RuntimeError(f"oracle_beamopt rc={rc}")
     return out

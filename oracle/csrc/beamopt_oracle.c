@@ -189,10 +189,26 @@ void oracle_adam_step_f32(const OracleBeamOptParams *p, int64_t n, float neg_ste
 /* the loop                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 
+/* fe_precision: 0 = FP64 dpbsv restatement (what the reference's OpenSees BandSPD computes),
+ * 1 = the same FE solve in x87 80-bit arithmetic ("truth" for arbitrating ill-conditioned beams). */
+int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
+                        const int32_t *force_nodes, const double *force_vals, const double *L,
+                        float *I_out, double *defl, double *rot, float *shear, float *moment,
+                        int32_t *epochs, float *loss, int32_t *status, int fe_precision);
+
 int oracle_beamopt(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
                    const int32_t *force_nodes, const double *force_vals, const double *L,
                    float *I_out, double *defl, double *rot, float *shear, float *moment,
                    int32_t *epochs, float *loss, int32_t *status)
+{
+    return oracle_beamopt_prec(p, B, fixed_uy, force_nodes, force_vals, L, I_out, defl, rot, shear, moment,
+                               epochs, loss, status, 0);
+}
+
+int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
+                        const int32_t *force_nodes, const double *force_vals, const double *L,
+                        float *I_out, double *defl, double *rot, float *shear, float *moment,
+                        int32_t *epochs, float *loss, int32_t *status, int fe_precision)
 {
     const int nn = p->num_nodes, n = nn - 1, C = p->num_cases, F = p->max_forces;
     if (nn < 2 || C < 1 || F < 0) return -1;
@@ -201,7 +217,8 @@ int oracle_beamopt(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed
     double *I64 = malloc(sizeof(double) * (size_t)n);
     double *f_uy = malloc(sizeof(double) * (size_t)nn);
     double *V = malloc(sizeof(double) * (size_t)n), *M = malloc(sizeof(double) * (size_t)n);
-    double *work = malloc(sizeof(double) * fe_work_doubles_f64(nn));
+    void *work = fe_precision ? malloc(sizeof(long double) * fe_work_doubles_f80(nn))
+                              : malloc(sizeof(double) * fe_work_doubles_f64(nn));
     float *m = I + n, *v = I + 2 * n, *grad = I + 3 * n, *csq = I + 4 * n, *hsq = I + 5 * n, *scr = I + 6 * n;
     oracle_adam_schedule(p, table);
     for (int64_t b = 0; b < B; ++b) {
@@ -219,7 +236,10 @@ int oracle_beamopt(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed
                     if (nd >= 0 && nd < nn) f_uy[nd] += force_vals[(b * C + c) * F + j];
                 }
                 double *u_c = defl + (b * C + c) * nn, *r_c = rot + (b * C + c) * nn;
-                if (beam_fe_solve_f64(nn, I64, L[b], fx, f_uy, p->udl, p->E, u_c, r_c, V, M, work)) { st = 1; break; }
+                const int frc = fe_precision
+                    ? beam_fe_solve_f80(nn, I64, L[b], fx, f_uy, p->udl, p->E, u_c, r_c, V, M, work)
+                    : beam_fe_solve_f64(nn, I64, L[b], fx, f_uy, p->udl, p->E, u_c, r_c, V, M, work);
+                if (frc) { st = 1; break; }
                 float *Vc = shear + (b * C + c) * n, *Mc = moment + (b * C + c) * n;
                 for (int e = 0; e < n; ++e) {
                     Vc[e] = (float)V[e];

@@ -34,6 +34,10 @@ int oracle_beamopt(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed
                    const int32_t *force_nodes, const double *force_vals, const double *L,
                    float *I_out, double *defl, double *rot, float *shear, float *moment,
                    int32_t *epochs, float *loss, int32_t *status);
+int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
+                        const int32_t *force_nodes, const double *force_vals, const double *L,
+                        float *I_out, double *defl, double *rot, float *shear, float *moment,
+                        int32_t *epochs, float *loss, int32_t *status, int fe_precision);
 int oracle_beam_solve(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
                       const int32_t *force_nodes, const double *force_vals, const double *L,
                       const double *I, double *defl, double *rot, double *shear, double *moment,

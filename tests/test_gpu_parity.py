@@ -356,3 +356,21 @@ def test_columnar_dataset_and_trainer_preprocessing_on_device(tmp_path):
     pre = dataset.trainer_preprocess(back, n_cases=4, c=0.5, seed=0, device="cuda")
     assert pre["X_train"].is_cuda and pre["X_train"].shape[0] == int(0.8 * 24)
     assert pre["Y_train"].shape[1] == 100 + 101 + 101 and torch.isfinite(pre["Y_train"]).all()
+
+
+def test_random_bridges_against_the_80bit_fe_loop():
+    """flag=1 draws short, stiff spans whose K is ill conditioned: there the reference's FP64 banded
+    Cholesky (the FP64 oracle) is itself several digits away from the exact solve.  Against the same loop
+    with the FE half in 80-bit arithmetic the CUDA path must be at least as close as the FP64 oracle is."""
+    p = BeamOptParams.for_script("SC")
+    cases = seeded_cases(p, 1024, seed=2024, flag=1)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    t = oracle_run(p, fixed, fn, fv, L, 1)
+    o = oracle_run(p, fixed, fn, fv, L, 0)
+    g = gpu_run(p, fixed, fn, fv, L)
+    same_g, same_o = g["epochs"] == t["epochs"], o["epochs"] == t["epochs"]
+    assert (~same_g).sum() <= max((~same_o).sum(), 2)
+    both = same_g & same_o
+    err_g = np.max(np.abs(g["I"][both] - t["I"][both]) / t["I"][both])
+    err_o = np.max(np.abs(o["I"][both] - t["I"][both]) / t["I"][both])
+    assert err_g < 1e-5 and err_g <= 2 * err_o + 1e-7, (err_g, err_o)
