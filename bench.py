@@ -244,7 +244,9 @@ def run_ours(args):
     select_workload(args.workload, world)
     p = workload_params()
     B = BEAMS_PER_GPU
+    t_s0 = time.perf_counter()
     fixed, fn, fv, L = sample_inputs(B, seed=1000 + rank)
+    sampling_s = time.perf_counter() - t_s0
     h_in = [torch.from_numpy(a).pin_memory() for a in (fixed, fn, fv, L)]
     d_in = [t.to(dev) for t in h_in]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -407,6 +409,10 @@ def run_ours(args):
         "early_stop_mode": {"value": B / (es_ms * 1e-3), "unit": UNIT, "kernel_ms": es_ms, "mean_epochs": es_epochs,
                             "note": "same beams with the MultiCore script's early stopping (tolerance 5e-3, patience "
                                     "10) instead of 600 fixed epochs; this rank only"},
+        "host_side": {"sampling_and_packing_s": sampling_s,
+                      "note": "Python `random` sampling of this rank's beams in the reference's draw order + packing "
+                              "into the ABI arrays; outside every timed region (SURVEY 7: host-side costs are reported "
+                              "separately)"},
         "cpu_baseline": cpu,
         "cpu_baseline_c": cpu_c,
     }

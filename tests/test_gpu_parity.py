@@ -374,3 +374,21 @@ def test_random_bridges_against_the_80bit_fe_loop():
     err_g = np.max(np.abs(g["I"][both] - t["I"][both]) / t["I"][both])
     err_o = np.max(np.abs(o["I"][both] - t["I"][both]) / t["I"][both])
     assert err_g < 1e-5 and err_g <= 2 * err_o + 1e-7, (err_g, err_o)
+
+
+@pytest.mark.parametrize("num_nodes", [6, 33, 64, 87, 129, 169])
+def test_other_discretisations(num_nodes):
+    """Every template instance of the lanes kernel (4 / 8 / 13 / 21 element slots per lane, run-time n)."""
+    p = BeamOptParams.for_script("SC").replace(num_nodes=num_nodes, max_e=60)
+    n = num_nodes - 1
+    rollers = sorted({max(2, int(round(f * n))) for f in (0.1, 0.3, 0.7, 0.85)} | {n})
+    cases = seeded_cases(p, 300, seed=num_nodes, roller_nodes=rollers)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    a, b = oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L)
+    assert not b["status"].any()
+    same = a["epochs"] == b["epochs"]
+    assert same.mean() >= 0.99
+    assert np.max(np.abs(a["I"][same] - b["I"][same]) / a["I"][same]) < 1e-5
+    assert (a["loss"][same] == b["loss"][same]).mean() > 0.95
+    assert rel_err(b["moment"][same, 0], a["moment"][same, 0]).max() < 1e-6
+    assert rel_err(b["defl"][same, 0], a["defl"][same, 0]).max() < 1e-6

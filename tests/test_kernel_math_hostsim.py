@@ -159,3 +159,21 @@ def test_shared_inertia_load_cases_against_c_oracle(num_cases):
     for key in ("defl", "rot", "moment", "shear"):
         assert rel_err(b[key].reshape(B * num_cases, -1), a[key].reshape(B * num_cases, -1)).max() < 1e-6, key
     assert (b["defl"][:, :, -1] == 0).all()
+
+
+@pytest.mark.parametrize("num_nodes", [6, 33, 64, 87, 129, 169])
+def test_other_discretisations_against_c_oracle(num_nodes):
+    """Every template instance of the lanes kernel (4 / 8 / 13 / 21 element slots per lane) and the torch.sum
+    shapes that go with them (tails, left-over vectors, no full block at all)."""
+    p = BeamOptParams.for_script("SC").replace(num_nodes=num_nodes, max_e=60)
+    n = num_nodes - 1
+    rollers = sorted({max(2, int(round(f * n))) for f in (0.1, 0.3, 0.7, 0.85)} | {n})
+    cases = seeded_cases(p, 40, seed=num_nodes, roller_nodes=rollers)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    a = oracle_run(p, fixed, fn, fv, L)
+    b = hostsim_run(p, fixed, fn, fv, L, solver=0)
+    assert not a["status"].any() and not b["status"].any()
+    assert np.array_equal(a["epochs"], b["epochs"])
+    assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
+    assert (a["loss"] == b["loss"]).mean() > 0.95
+    assert rel_err(b["moment"][:, 0], a["moment"][:, 0]).max() < 1e-6
