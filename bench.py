@@ -73,10 +73,13 @@ BYTES_PER_BEAM = (NUM_NODES + 4 * 12 + 8) + (12 * (NUM_NODES - 1) + 16 * NUM_NOD
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 DFMA lanes/SM x 148 SMs x max SM clock
 
 
+SOLVER = 0
+
+
 def workload_params(early_stop=False):
     from openpystruct_b200.params import BeamOptParams
     return BeamOptParams.for_script("MC").replace(early_stop=early_stop, max_e=EPOCHS, num_nodes=NUM_NODES,
-                                                  num_cases=WL["num_cases"])
+                                                  num_cases=WL["num_cases"], solver=SOLVER)
 
 
 def sample_inputs(beams, seed):
@@ -242,6 +245,8 @@ def run_ours(args):
         WORKLOADS[args.workload]["beams"] = args.beams
         WORKLOADS[args.workload]["name"] += f" [beam count overridden: {args.beams}]"
     select_workload(args.workload, world)
+    global SOLVER
+    SOLVER = args.solver
     p = workload_params()
     B = BEAMS_PER_GPU
     t_s0 = time.perf_counter()
@@ -430,6 +435,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--beams", type=int, default=0, help="override the workload's total beam count (exploration only)")
+    ap.add_argument("--solver", type=int, default=0, help="OPS_SOLVER_* of the C ABI (exploration only; 0 = production)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -44,9 +44,12 @@ extern "C" {
 /* solver selection */
 #define OPS_SOLVER_THREE_MOMENT 0  /* exact Schur complement of K onto the support moments (default, fastest):
                                       eight lanes per beam with the optimiser state in registers for
-                                      num_nodes <= 169, else the thread-per-beam form */
+                                      num_nodes <= 169, else one warp per beam with the state in shared memory */
 #define OPS_SOLVER_BAND_LDLT    1  /* in-place banded (block) LDL^T of K, factor kept in shared memory */
 #define OPS_SOLVER_THREE_MOMENT_THREAD 2  /* three-moment, one thread per beam (any num_nodes) */
+#define OPS_SOLVER_THREE_MOMENT_SMEM8  3  /* three-moment, 8 lanes per beam, optimiser state in shared memory (num_nodes <= 169) */
+#define OPS_SOLVER_THREE_MOMENT_SMEM32 4  /* three-moment, one warp per beam, optimiser state in shared memory
+                                              (what OPS_SOLVER_THREE_MOMENT runs beyond 169 nodes) */
 
 /* Module-level constants of the reference generators (SingleCore:20-49, MultiCore:20-52, GPU:21-56,
  * BeamOpt:24-48) plus the literals of the loss (SingleCore:195-196) and torch's Adam defaults. */

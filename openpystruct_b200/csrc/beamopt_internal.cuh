@@ -39,6 +39,17 @@ bool lanes_supported(const BeamConsts &k, int num_cases);
 int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_optin, LanesPlan *pl);
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream);
 
+// shared-memory-state three-moment kernels, 8 or 32 lanes per beam (beamopt_wide.cu)
+struct WidePlan {
+    int lpb;             // lanes per beam
+    int beam_bytes;      // shared memory of one beam
+    int threads, blocks;
+    size_t smem_bytes;
+};
+bool wide_supported(const BeamConsts &k, int num_cases, int lpb, int smem_optin);
+int wide_plan(const BeamConsts &k, int lpb, int64_t B, int sms, int smem_optin, WidePlan *pl);
+cudaError_t wide_launch(const BeamConsts &k, long long B, const OptPtrs &p, const WidePlan &pl, cudaStream_t stream);
+
 // fastmath.cuh against the compiler's IEEE operators; out4 = {div mismatches, sqrt mismatches,
 // reciprocal mismatches, samples}
 cudaError_t fastmath_selftest(long long samples, unsigned long long *host_out4, double *worst_rcp64,

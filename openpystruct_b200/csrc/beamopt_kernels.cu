@@ -347,7 +347,8 @@ static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
         return OPS_E_UNSUPP;       // shared-I load cases: 2, 4 or 8 per beam, lanes kernel only
     if (p->max_forces > 8) return OPS_E_UNSUPP;
     if (p->solver != OPS_SOLVER_THREE_MOMENT && p->solver != OPS_SOLVER_BAND_LDLT &&
-        p->solver != OPS_SOLVER_THREE_MOMENT_THREAD)
+        p->solver != OPS_SOLVER_THREE_MOMENT_THREAD && p->solver != OPS_SOLVER_THREE_MOMENT_SMEM8 &&
+        p->solver != OPS_SOLVER_THREE_MOMENT_SMEM32)
         return OPS_E_BADARG;
     if (p->reserved != 0) return OPS_E_BADARG;
     k->nn = p->num_nodes;
@@ -378,6 +379,8 @@ static int make_consts(const OpsBeamOptParams *p, BeamConsts *k)
 struct LaunchPlan {
     bool lanes;          // eight-lanes-per-beam three-moment kernel (beamopt_lanes.cu)
     LanesPlan lp;
+    bool wide;           // shared-memory-state three-moment kernels (beamopt_wide.cu)
+    WidePlan wp;
     bool flex;           // thread-per-beam three-moment kernel
     FlexLayout lay;
     bool smem;
@@ -451,6 +454,17 @@ static int plan_launch(const BeamConsts &k, int num_cases, int64_t B, int solver
         return lanes_plan(k, num_cases, B, sms, smem_optin, &pl->lp);
     }
     if (num_cases != 1) return OPS_E_UNSUPP;
+    {
+        // fine discretisations run one warp per beam; the explicit selectors pick a lane count
+        const int lpb = solver == OPS_SOLVER_THREE_MOMENT_SMEM8 ? 8 :
+                        ((solver == OPS_SOLVER_THREE_MOMENT_SMEM32 || solver == OPS_SOLVER_THREE_MOMENT) ? 32 : 0);
+        if (lpb && wide_supported(k, num_cases, lpb, smem_optin)) {
+            memset(pl, 0, sizeof *pl);
+            pl->wide = true;
+            return wide_plan(k, lpb, B, sms, smem_optin, &pl->wp);
+        }
+        if (solver == OPS_SOLVER_THREE_MOMENT_SMEM8 || solver == OPS_SOLVER_THREE_MOMENT_SMEM32) return OPS_E_UNSUPP;
+    }
     if (solver == OPS_SOLVER_THREE_MOMENT || solver == OPS_SOLVER_THREE_MOMENT_THREAD)
         return plan_flex(k, B, sms, smem_optin, pl);
     const size_t pb = per_beam_bytes(k.nn);
@@ -621,6 +635,10 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
         e = lanes_launch(k, (long long)B, q, pl.lp, stream);
         return e == cudaSuccess ? 0 : (int)e;
     }
+    if (pl.wide) {
+        e = wide_launch(k, (long long)B, q, pl.wp, stream);
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     if (pl.flex) {
         e = cudaFuncSetAttribute(beamopt_flex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)pl.smem_bytes);
@@ -670,7 +688,7 @@ int ops_beamsolve_launch(const OpsBeamOptParams *p, int64_t B,
     q.fixed_uy = fixed_uy; q.force_nodes = force_nodes; q.force_vals = force_vals; q.L = L; q.I = I_f64;
     q.defl = deflections; q.rot = rotations; q.shear = shear; q.moment = moment; q.status = status;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    if (p->solver == OPS_SOLVER_THREE_MOMENT || p->solver == OPS_SOLVER_THREE_MOMENT_THREAD) {
+    if (p->solver != OPS_SOLVER_BAND_LDLT) {
         const int threads = 64;
         const size_t smem = (size_t)threads * (FlexStore::NUM_DOUBLES * 8 + FlexStore::NUM_INTS * 4);
         e = cudaFuncSetAttribute(beamsolve_flex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

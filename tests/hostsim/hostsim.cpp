@@ -341,3 +341,136 @@ extern "C" int hostsim_beamopt_lanes(const OpsBeamOptParams *p, int64_t B, const
 #undef RUN
     return OPS_E_UNSUPP;
 }
+
+// Shared-memory-state iteration (beamopt_wide.cuh) with the control flow of beamopt_wide_kernel: the
+// per-lane functions are the device code itself, run lane by lane; the two cross-lane steps (butterfly
+// sum of a closing span, final loss combine) are done on arrays here and with shuffles on the device.
+#include "../../openpystruct_b200/csrc/beamopt_wide.cuh"
+
+template <int LPB, int N>
+static void wide_host_batch(const BeamConsts &k, const FlexBeam &fb, const ops::wide::WideShape &sh,
+                            const ops::wide::WideStore &ws, int kb, bool run, const float *Icur, float *Inew,
+                            const ops::wide::SweepConsts &sc, ops::wide::LaneCtx<LPB> *cx)
+{
+    using namespace ops::wide;
+    static BatchOut<N> bo[LPB];
+    for (int l = 0; l < LPB; ++l) sweep_batch<LPB, N>(k, fb, sh, ws, l, kb, run, Icur, Inew, sc, cx[l], bo[l]);
+    for (int i = 0; i < N; ++i) {
+        double x[LPB][NSUM], aold[LPB][NSUM];
+        int sold[LPB];
+        for (int l = 0; l < LPB; ++l) {
+            slot_terms<N>(bo[l], i, x[l]);
+            slot_accumulate<LPB>(cx[l], x[l], bo[l].sp[i], aold[l], sold[l]);
+        }
+        if (!bo[0].close[i]) continue;
+        for (int j = 0; j < NSPAN; ++j) {
+            if (ws.gi[GI_CLOSE + j] != kb + i) continue;
+            double v[LPB][NSUM];
+            for (int l = 0; l < LPB; ++l) close_value(aold[l], sold[l], x[l], bo[l].sp[i], j, v[l]);
+            for (int step = 1; step < LPB; step <<= 1) {              // butterfly: v_l += v_{l ^ step}
+                double nv[LPB][NSUM];
+                for (int l = 0; l < LPB; ++l)
+                    for (int w = 0; w < NSUM; ++w) nv[l][w] = v[l][w] + v[l ^ step][w];
+                memcpy(v, nv, sizeof v);
+            }
+            for (int w = 0; w < NSUM; ++w) ws.tot[j * NSUM + w] = v[0][w];
+        }
+    }
+}
+
+template <int LPB>
+static void wide_host_sweep(const BeamConsts &k, const FlexBeam &fb, const ops::wide::WideShape &sh,
+                            const ops::wide::WideStore &ws, bool run, const float *Icur, float *Inew,
+                            const ops::wide::SweepConsts &sc, ops::wide::LaneCtx<LPB> *cx)
+{
+    using namespace ops::wide;
+    for (int l = 0; l < LPB; ++l) ctx_reset<LPB>(cx[l], l);
+    int kb = 0;
+    for (; kb + NB <= sh.K; kb += NB) wide_host_batch<LPB, NB>(k, fb, sh, ws, kb, run, Icur, Inew, sc, cx);
+    for (; kb < sh.K; ++kb) wide_host_batch<LPB, 1>(k, fb, sh, ws, kb, run, Icur, Inew, sc, cx);
+    for (int l = 0; l < LPB; ++l) ctx_finish<LPB>(sh, cx[l]);
+}
+
+template <int LPB>
+static int wide_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, const int32_t *force_nodes,
+                    const double *force_vals, const double *L, const float *sched, float *I_values, double *defl,
+                    double *rot, float *shear, float *moment, int32_t *epochs, float *loss, int32_t *status)
+{
+    using namespace ops::wide;
+    const int n = k.n, nn = k.nn;
+    if (!wide_shape_ok<LPB>(n)) return OPS_E_UNSUPP;
+    const WideShape sh = wide_shape<LPB>(n);
+    std::vector<double> raw(wide_beam_bytes<LPB>(n) / 8 + 2);
+    WideStore ws;
+    wide_carve<LPB>(reinterpret_cast<unsigned char *>(raw.data()), n, ws);
+    static LaneCtx<LPB> cx[LPB];
+    for (int64_t b = 0; b < B; ++b) {
+        int fnode[FLEX_MAXF];
+        double fval[FLEX_MAXF];
+        for (int j = 0; j < k.max_forces; ++j) {
+            fnode[j] = force_nodes[b * k.max_forces + j];
+            fval[j] = force_vals[b * k.max_forces + j];
+        }
+        const uint8_t *fx = fixed_uy + b * nn;
+        wide_setup<LPB>(k, L[b], [&](int i) { return fx[i] != 0; }, fnode, fval, ws);
+        FlexBeam fb;
+        int bad = wide_fetch(k, L[b], ws, fb);
+        const bool setup_bad = bad != 0;
+        SweepConsts sc;
+        sc.G2 = 6.0 * fb.wl2h; sc.H2 = 3.0 * fb.wl2h; sc.neg_step = 0.0f; sc.bc2_sqrt = 1.0f; sc.rbc = 1.0f;
+        if (!bad) {
+            for (int l = 0; l < LPB; ++l) wide_lane_init<LPB>(k, sh, ws, l);
+            wide_host_sweep<LPB>(k, fb, sh, ws, false, ws.I0, ws.I0 + ws.el, sc, cx);
+        }
+        int t = 0, counter = 0;
+        double best = INFINITY;
+        float lossf = NAN;
+        bool done = (k.max_epochs <= 0) || bad;
+        while (!done) {
+            sc.neg_step = sched[2 * t]; sc.bc2_sqrt = sched[2 * t + 1]; sc.rbc = 1.0f / sc.bc2_sqrt;
+            int rc = 0;
+            for (int l = LPB - 1; l >= 0; --l) rc |= wide_solve<LPB>(fb, ws, l);
+            wide_host_sweep<LPB>(k, fb, sh, ws, true, ws.I0 + (t & 1) * ws.el, ws.I0 + ((t + 1) & 1) * ws.el, sc, cx);
+            float acc[3][LPB], left[3][LPB];
+            for (int w = 0; w < 3; ++w)
+                for (int l = 0; l < LPB; ++l) {
+                    acc[w][l] = LPB == 32 ? cx[l].acc[w][0] : ctx_rowsum<LPB>(cx[l], w);
+                    left[w][l] = cx[l].left[w];
+                }
+            lossf = wide_loss_arrays<LPB>(k, sh, acc, left);
+            ++t;
+            if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
+            if (k.early_stop) {
+                const double l_ = (double)lossf;
+                if (l_ < best - k.tol) { best = l_; counter = 0; } else { ++counter; }
+                if (counter >= k.patience) done = true;
+            }
+            if (t >= k.max_epochs) done = true;
+        }
+        const bool fields = (t > 0) && (bad == 0);
+        for (int l = 0; l < LPB; ++l)
+            wide_emit_lane<LPB>(fb, sh, ws, l, fields, ws.I0 + (t & 1) * ws.el, shear + b * n, moment + b * n,
+                                setup_bad ? nullptr : I_values + b * n);
+        if (setup_bad) for (int e = 0; e < n; ++e) I_values[b * n + e] = k.I0f;
+        wide_emit_displacements(k, fb, ws, ws.I0 + ((t + 1) & 1) * ws.el, fields, defl + b * nn, rot + b * nn);
+        epochs[b] = t; loss[b] = lossf; status[b] = bad;
+    }
+    return 0;
+}
+
+extern "C" int hostsim_beamopt_wide(const OpsBeamOptParams *p, int lanes_per_beam, int64_t B, const uint8_t *fixed_uy,
+                                    const int32_t *force_nodes, const double *force_vals, const double *L,
+                                    const float *sched, float *I_values, double *defl, double *rot,
+                                    float *shear, float *moment, int32_t *epochs, float *loss, int32_t *status)
+{
+    if (p->num_cases != 1 || p->max_forces > FLEX_MAXF) return OPS_E_UNSUPP;
+    BeamConsts k;
+    consts_from(p, &k);
+    if (lanes_per_beam == 8)
+        return wide_run<8>(k, B, fixed_uy, force_nodes, force_vals, L, sched, I_values, defl, rot, shear, moment, epochs,
+                           loss, status);
+    if (lanes_per_beam == 32)
+        return wide_run<32>(k, B, fixed_uy, force_nodes, force_vals, L, sched, I_values, defl, rot, shear, moment, epochs,
+                            loss, status);
+    return OPS_E_UNSUPP;
+}

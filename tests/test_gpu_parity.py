@@ -16,9 +16,11 @@ from tests.helpers import (goldens, golden_params, golden_case, oracle_params, o
 pytestmark = pytest.mark.gpu
 
 # the device solvers behind the same ABI: 0 = three-moment, 8 lanes per beam (production default),
-# 1 = banded LDL^T, 2 = three-moment, thread per beam
+# 1 = banded LDL^T, 2 = three-moment, thread per beam, 3 / 4 = three-moment with the optimiser state in
+# shared memory, 8 / 32 lanes per beam (4 is what solver 0 runs beyond 169 nodes)
 SOLVERS = [pytest.param(0, id="three_moment_lanes"), pytest.param(1, id="band_ldlt"),
-           pytest.param(2, id="three_moment_thread")]
+           pytest.param(2, id="three_moment_thread"), pytest.param(3, id="three_moment_smem8"),
+           pytest.param(4, id="three_moment_smem32")]
 
 
 def gpu_run(p, fixed, fn, fv, L):
@@ -268,15 +270,18 @@ def test_three_moment_unsupported_roller_count_and_ldlt_fallback():
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
     assert gpu_run(p.replace(solver=0), fixed, fn, fv, L)["status"][0] == 3
     assert gpu_run(p.replace(solver=2), fixed, fn, fv, L)["status"][0] == 3
+    assert gpu_run(p.replace(solver=3), fixed, fn, fv, L)["status"][0] == 3
+    assert gpu_run(p.replace(solver=4), fixed, fn, fv, L)["status"][0] == 3
     b = gpu_run(p.replace(solver=1), fixed, fn, fv, L)
     a = oracle_run(p, fixed, fn, fv, L)
     assert b["status"][0] == 0 and np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
 
 
-def test_fine_discretisation_1000_elements():
+@pytest.mark.parametrize("solver", [0, 2])
+def test_fine_discretisation_1000_elements(solver):
     """BASELINE config 5 geometry (1001 nodes, rollers x10): the three-moment solve stays within 1e-9 of
     the 80-bit truth where FP64 banded Cholesky cannot (cond(K) ~ 2e10), and the loop matches the oracle."""
-    p = BeamOptParams.for_script("MC").replace(num_nodes=1001, max_e=12, solver=0)
+    p = BeamOptParams.for_script("MC").replace(num_nodes=1001, max_e=12, solver=solver)
     cases = seeded_cases(p, 64, seed=31, roller_nodes=[100, 300, 700, 850, 1000])
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
     a, b = oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L)
@@ -376,10 +381,12 @@ def test_random_bridges_against_the_80bit_fe_loop():
     assert err_g < 1e-5 and err_g <= 2 * err_o + 1e-7, (err_g, err_o)
 
 
+@pytest.mark.parametrize("solver", [0, 3, 4])
 @pytest.mark.parametrize("num_nodes", [6, 33, 64, 87, 129, 169])
-def test_other_discretisations(num_nodes):
-    """Every template instance of the lanes kernel (4 / 8 / 13 / 21 element slots per lane, run-time n)."""
-    p = BeamOptParams.for_script("SC").replace(num_nodes=num_nodes, max_e=60)
+def test_other_discretisations(num_nodes, solver):
+    """Every template instance of the lanes kernel (4 / 8 / 13 / 21 element slots per lane, run-time n) and of the
+    shared-memory-state kernels."""
+    p = BeamOptParams.for_script("SC").replace(num_nodes=num_nodes, max_e=60, solver=solver)
     n = num_nodes - 1
     rollers = sorted({max(2, int(round(f * n))) for f in (0.1, 0.3, 0.7, 0.85)} | {n})
     cases = seeded_cases(p, 300, seed=num_nodes, roller_nodes=rollers)

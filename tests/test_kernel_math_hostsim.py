@@ -13,7 +13,8 @@ from tests.helpers import (goldens, golden_params, golden_case, hostsim_run, hos
 
 
 SOLVERS = [pytest.param(0, id="three_moment_lanes"), pytest.param(1, id="band_ldlt"),
-           pytest.param(2, id="three_moment_thread")]
+           pytest.param(2, id="three_moment_thread"), pytest.param(3, id="three_moment_smem8"),
+           pytest.param(4, id="three_moment_smem32")]
 
 
 @pytest.mark.parametrize("solver", SOLVERS)
@@ -122,10 +123,11 @@ def test_three_moment_reports_unsupported_roller_count():
     assert b["status"][0] == 0 and np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
 
 
-def test_fine_discretisation_1000_elements_three_moment():
+@pytest.mark.parametrize("solver", [2, 4])
+def test_fine_discretisation_1000_elements_three_moment(solver):
     """BASELINE config 5 geometry: 1001 nodes, rollers scaled x10; exercises the torch.sum level cascade
     (n >= 512) and the O(#supports) state.  Compared with the 80-bit truth / the fp32 oracle loop."""
-    p = BeamOptParams.for_script("MC").replace(num_nodes=1001, max_e=12, solver=0)
+    p = BeamOptParams.for_script("MC").replace(num_nodes=1001, max_e=12, solver=solver)
     cases = seeded_cases(p, 6, seed=31, roller_nodes=[100, 300, 700, 850, 1000])
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
     a = oracle_run(p, fixed, fn, fv, L)
@@ -161,8 +163,9 @@ def test_shared_inertia_load_cases_against_c_oracle(num_cases):
     assert (b["defl"][:, :, -1] == 0).all()
 
 
+@pytest.mark.parametrize("solver", [0, 3, 4])
 @pytest.mark.parametrize("num_nodes", [6, 33, 64, 87, 129, 169])
-def test_other_discretisations_against_c_oracle(num_nodes):
+def test_other_discretisations_against_c_oracle(num_nodes, solver):
     """Every template instance of the lanes kernel (4 / 8 / 13 / 21 element slots per lane) and the torch.sum
     shapes that go with them (tails, left-over vectors, no full block at all)."""
     p = BeamOptParams.for_script("SC").replace(num_nodes=num_nodes, max_e=60)
@@ -171,7 +174,7 @@ def test_other_discretisations_against_c_oracle(num_nodes):
     cases = seeded_cases(p, 40, seed=num_nodes, roller_nodes=rollers)
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
     a = oracle_run(p, fixed, fn, fv, L)
-    b = hostsim_run(p, fixed, fn, fv, L, solver=0)
+    b = hostsim_run(p, fixed, fn, fv, L, solver=solver)
     assert not a["status"].any() and not b["status"].any()
     assert np.array_equal(a["epochs"], b["epochs"])
     assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
