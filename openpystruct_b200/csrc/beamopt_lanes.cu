@@ -137,41 +137,49 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             }
         }
         if (!__any_sync(0xffffffffu, have)) break;
-        if (have) {
-            bool done = (k.max_epochs <= 0) || (bad != 0);
-            float neg_step = 0.0f, bc2_sqrt = 1.0f;
-            if (!done) {
-                neg_step = __ldg(p.sched + 2 * t);
-                bc2_sqrt = __ldg(p.sched + 2 * t + 1);
-                __syncwarp(gmask);
-                lane_reduce(l, fb.m, ls, gs);
-                __syncwarp(gmask);
-                const int rc = group_solve(fb, gs, l);
-                __syncwarp(gmask);
-                if (NC > 1) {
-                    lane_case_squares<EPL>(rg, ls, gs);
-                    team_sync<NC>(team_mask, barrier_id);
-                }
-                lane_forces<EPL, NC>(k, n, rg, ls, gs, l, case_id);
-                if (NC > 1) team_sync<NC>(team_mask, barrier_id);   // exchange columns are rewritten next epoch
-                else __syncwarp(gmask);
-                lossf = group_loss(k, n, ls, l);
-                ++t;
-                if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
-                if (k.early_stop) {
-                    const double lv = (double)lossf;
-                    if (lv < best - k.tol) { best = lv; counter = 0; } else { ++counter; }
-                    if (counter >= k.patience) done = true;
-                }
-                if (t >= k.max_epochs) done = true;
+        // One epoch.  The phases are separated by FULL-warp barriers that every lane reaches (a group without
+        // a running beam only keeps the appointment): a barrier on the group's own 8-lane mask is a
+        // non-uniform mask, which costs a MATCH / REDUX / VOTE sequence per barrier instead of nothing.
+        const bool run = have && k.max_epochs > 0 && bad == 0;
+        bool done = have && !run;
+        float neg_step = 0.0f, bc2_sqrt = 1.0f;
+        int rc = 0;
+        if (run) {
+            neg_step = __ldg(p.sched + 2 * t);
+            bc2_sqrt = __ldg(p.sched + 2 * t + 1);
+        }
+        __syncwarp();
+        if (run) lane_reduce(l, fb.m, ls, gs);
+        __syncwarp();
+        if (run) rc = group_solve(fb, gs, l);
+        __syncwarp();
+        if (NC > 1) {
+            if (run) lane_case_squares<EPL>(rg, ls, gs, fb.invLe);
+            if (NC * LPB <= 32) __syncwarp();
+            else if (run) team_sync<NC>(team_mask, barrier_id);    // whole warps belong to one team: uniform
+        }
+        if (run) lane_forces<EPL, NC>(k, n, rg, ls, gs, fb.invLe, l, case_id);
+        if (NC * LPB <= 32) __syncwarp();                           // (NC > 1: exchange columns are rewritten next epoch)
+        else if (run) team_sync<NC>(team_mask, barrier_id);
+        if (run) {
+            lossf = group_loss(k, n, ls, l);
+            ++t;
+            if (rc || !(lossf - lossf == 0.0f)) { bad = 1; done = true; }
+            if (k.early_stop) {
+                const double lv = (double)lossf;
+                if (lv < best - k.tol) { best = lv; counter = 0; } else { ++counter; }
+                if (counter >= k.patience) done = true;
             }
+            if (t >= k.max_epochs) done = true;
+        }
+        if (have) {
             if (!done) {
                 lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
             } else {
                 // record of the beam: fields of the last analysed inertias, then the last Adam step
                 const bool fields = (t > 0) && (bad == 0);
                 const long long bc = b * NC + case_id;
-                lane_emit_forces<EPL>(n, rg, ls, gs, l, fields, p.shear + bc * n, p.moment + bc * n);
+                lane_emit_forces<EPL>(n, rg, ls, gs, fb.invLe, l, fields, p.shear + bc * n, p.moment + bc * n);
                 __syncwarp(gmask);
                 if (l == 0) {
                     LaneStore ls0 = ls;

@@ -48,8 +48,8 @@ constexpr int DUMMY = NSPAN;                    // span id of overhang elements 
 constexpr int NSUM = 5;                         // R0, R1, R2, G, Q
 constexpr int SCR_STAGE = NSPAN * NSUM;         // 3 slots after the partial sums: {row sum, tail} of sum I, d, q
 constexpr int SCR_SLOTS = SCR_STAGE + 3;
-constexpr int TAB_T2 = 2 * (NSPAN + 1);         // span table: Pair {MS_l, (MS_r - MS_l) d} [6], then (MS_r - MS_l) d / Le [6]
-constexpr int TAB_SLOTS = 3 * (NSPAN + 1) + 2;  // contiguous per group; +2 keeps the four groups of a warp on distinct banks
+constexpr int TAB_SLOTS = 2 * (NSPAN + 1);      // span table, contiguous per group: Pair {MS_l, (MS_r - MS_l) d} [6], 16-byte rows (a
+                                                // 128-bit access is served per quarter warp = per group: no bank conflicts between groups)
 constexpr int GX_DOUBLES = 2;                   // Moh, Qoh
 constexpr int GX_INTS = 6;                      // m, last, nloads, setup status, beam index of the team (lo, hi)
 constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + GX_DOUBLES;   // strided [slot][group] columns (+ TAB_SLOTS contiguous)
@@ -83,7 +83,7 @@ struct LaneStore {
 // per-group shared data: strided columns (entry k at base[k * gs]) and the contiguous span table
 struct GroupStore {
     FlexStore fs;                               // supports, loads, RA, DXI; slots A..Q hold a, b, c, p, q (no Le/6E)
-    double *tab;                                // [TAB_SLOTS] contiguous, 16-byte aligned
+    double *tab;                                // [TAB_SLOTS] contiguous, 16-byte aligned (TAB_ALIGN on the device)
     double *gd;                                 // [GX_DOUBLES]
     int *gi;                                    // [GX_INTS]
     long gs;
@@ -101,6 +101,16 @@ OPS_HD SumShape sum_shape(int n)
     s.blk = (s.vec / 4) * 4;
     s.ntail = n - 8 * s.vec;
     return s;
+}
+
+// byte offset of the span-table row of slot kk (16 j, j = span id of the slot): one shift and one mask
+OPS_HD unsigned int row_offset(unsigned long long spans, int kk)
+{
+    return (3 * kk >= 4) ? ((unsigned int)(spans >> (3 * kk - 4)) & 0x70u) : ((unsigned int)(spans << (4 - 3 * kk)) & 0x70u);
+}
+OPS_HD Pair table_row(const double *tab, unsigned int off)
+{
+    return *reinterpret_cast<const Pair *>(reinterpret_cast<const char *>(tab) + off);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,9 +292,11 @@ OPS_HD void lane_reduce(int l, int m, const LaneStore &ls, const GroupStore &gs)
 
 // Three-moment system for the support moments (every lane, redundantly): unknowns MS[1..m-1],
 // MS[0] = 0 (pinned end), MS[m] = overhang moment, Thomas elimination written without data-dependent
-// control flow (rows kk >= m are computed on zeros and discarded by a select; every array index is a
-// compile-time constant, so the working set stays in registers).  Lane 0 publishes the per-span table
-// PASS 2 reads.  Returns 1 when a pivot of a real row is not positive.
+// control flow: rows kk >= m are computed on the zeros lane_reduce leaves for unused spans (they may
+// come out Inf / NaN, feed only later unused rows in the forward sweep and are discarded by the one
+// select of the back substitution); every array index is a compile-time constant, so the working set
+// stays in registers.  Lane 0 publishes the per-span table PASS 2 reads (rows j >= m are never read:
+// no element carries such a span id).  Returns 1 when a pivot of a real row is not positive.
 OPS_HD int group_solve(const FlexBeam &fb, const GroupStore &gs, int l)
 {
     const int m = fb.m;
@@ -312,9 +324,7 @@ OPS_HD int group_solve(const FlexBeam &fb, const GroupStore &gs, int l)
             dd = fma(-w, bk, dd);
             r_ = fma(-w, rp, r_);
         }
-        const bool live = kk < m;
-        bad = bad || (live && !(dd > 0.0));
-        dd = live ? dd : 1.0;
+        bad = bad || (kk < m && !(dd > 0.0));
         ip = fm::rcp64(dd);
         rp = r_;
         inv[kk] = ip; rr[kk] = r_;
@@ -329,13 +339,9 @@ OPS_HD int group_solve(const FlexBeam &fb, const GroupStore &gs, int l)
 #pragma unroll
         for (int j = 0; j < NSPAN; ++j) {
             const double dxj = gs.fs.span(j + 1, FlexStore::DXI);
-            const bool live = j < m;
-            const double dM = MS[j + 1] - MS[j];
-            const double t1 = live ? dM * dxj : 0.0;
             Pair lo;
-            lo.x = live ? MS[j] : 0.0; lo.y = t1;
+            lo.x = MS[j]; lo.y = (MS[j + 1] - MS[j]) * dxj;
             reinterpret_cast<Pair *>(gs.tab)[j] = lo;
-            gs.tab[TAB_T2 + j] = t1 * fb.invLe;
         }
         // the DUMMY row (overhang, padding) stays zero: written once per beam by group_table_init
     }
@@ -349,15 +355,13 @@ OPS_HD void group_table_init(const GroupStore &gs)
 
 // bending moment (three-moment sign: sagging positive) and shear at the node-i end of slot kk
 template <int EPL>
-OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, int kk,
+OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe, int kk,
                            double &Mc, double &Qv)
 {
-    const int j = (int)((rg.spans >> (3 * kk)) & 7u);
-    const Pair lo = reinterpret_cast<const Pair *>(gs.tab)[j];
-    const double t2 = gs.tab[TAB_T2 + j];
+    const Pair lo = table_row(gs.tab, row_offset(rg.spans, kk));
     const Pair mq = ls.mq[(long)kk * ls.ls];
     Mc = fma(lo.y, (double)rg.ke[kk], mq.x + lo.x);
-    Qv = mq.y + t2;
+    Qv = fma(lo.y, invLe, mq.y);
 }
 
 // Elements are processed in batches of NB slots, STAGE BY STAGE across the batch: the stages of one
@@ -371,12 +375,12 @@ constexpr int NB = OPS_LANES_NB;
 
 // multi-case kernels, before PASS 2: M^2, V^2 of this group's load case into the exchange column
 template <int EPL>
-OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs)
+OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe)
 {
 #pragma unroll
     for (int kk = 0; kk < EPL; ++kk) {
         double Mc, Qv;
-        element_forces<EPL>(rg, ls, gs, kk, Mc, Qv);
+        element_forces<EPL>(rg, ls, gs, invLe, kk, Mc, Qv);
         const float Mf = (float)Mc, Vf = (float)Qv;
         PairF x;
         x.c = Mf * Mf; x.h = Vf * Vf;
@@ -390,8 +394,8 @@ OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, cons
 // fp32 ranges for the branch-free division / square root: I in [clamp_min, 1e20) (the clamp,
 // SingleCore:208), c = M^2 and h = V^2 zero or >= 2^-100.
 template <int EPL, int NC>
-OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, int l,
-                        int case_id)
+OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe,
+                        int l, int case_id)
 {
     const SumShape sh = sum_shape(n);
     float aI[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ad[4] = {0.0f, 0.0f, 0.0f, 0.0f}, aq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -407,15 +411,13 @@ OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const Lan
         OPS_B I[i] = rg.I[k0 + i];
         if (NC == 1) {
             Pair lo[NB], mq[NB];
-            double tq2[NB], ke[NB], Mc[NB], Qv[NB];
+            double ke[NB], Mc[NB], Qv[NB];
             OPS_B {
-                const int j = (int)((rg.spans >> (3 * (k0 + i))) & 7u);
-                lo[i] = reinterpret_cast<const Pair *>(gs.tab)[j];
-                tq2[i] = gs.tab[TAB_T2 + j];
+                lo[i] = table_row(gs.tab, row_offset(rg.spans, k0 + i));
                 mq[i] = ls.mq[(long)(k0 + i) * ls.ls];
                 ke[i] = (double)rg.ke[k0 + i];
             }
-            OPS_B { Mc[i] = mq[i].x + lo[i].x; Qv[i] = mq[i].y + tq2[i]; }
+            OPS_B { Mc[i] = mq[i].x + lo[i].x; Qv[i] = fma(lo[i].y, invLe, mq[i].y); }
             OPS_B Mc[i] = fma(lo[i].y, ke[i], Mc[i]);
             OPS_B { c[i] = (float)Mc[i]; h[i] = (float)Qv[i]; }
             OPS_B { c[i] = c[i] * c[i]; h[i] = h[i] * h[i]; }
@@ -522,7 +524,9 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &l
 #define OPS_A _Pragma("unroll") for (int kk = 0; kk < EPL; ++kk)
         OPS_A { t0[kk] = rg.g[kk] - rg.m[kk]; t1[kk] = k.omb2f * rg.g[kk]; rg.v[kk] = rg.v[kk] * k.b2f; }
         OPS_A { rg.m[kk] = fmaf(k.w1, t0[kk], rg.m[kk]); rg.v[kk] = fmaf(t1[kk], rg.g[kk], rg.v[kk]); }
-        OPS_A rare = rare || !(rg.v[kk] >= fm::SQRT_F_MIN);
+        float vmin = rg.v[0];
+        OPS_A vmin = fminf(vmin, rg.v[kk]);                         // (v is never NaN here: the loss was finite)
+        rare = !(vmin >= fm::SQRT_F_MIN);
 #undef OPS_A
     }
     if (!rare) {
@@ -550,7 +554,7 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &l
             OPS_B t1[i] = fmaf(-den[i], t0[i], num[i]);
             OPS_B t0[i] = fmaf(rd[i], t1[i], t0[i]);
             OPS_B t0[i] = rg.I[k0 + i] + t0[i];
-            OPS_B rg.I[k0 + i] = t0[i] < k.clampf ? k.clampf : t0[i];
+            OPS_B rg.I[k0 + i] = fmaxf(t0[i], k.clampf);           // one FMNMX (t0 is finite: den > 0, v and m finite)
             if (PASS1) {
                 double e[NB];
                 OPS_B Id[i] = (double)rg.I[k0 + i];
@@ -590,7 +594,7 @@ OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &l
 // inertias, i.e. the ones still in rg.I when the stop decision is taken (before lane_adam).
 // ---------------------------------------------------------------------------------------------
 template <int EPL>
-OPS_HD void lane_emit_forces(int n, const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, int l,
+OPS_HD void lane_emit_forces(int n, const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe, int l,
                              bool fields, float *shear, float *moment)
 {
     float *stage = reinterpret_cast<float *>(ls.scr);        // I of slot kk at float index (kk >> 1) * 2 ls + (kk & 1)
@@ -600,7 +604,7 @@ OPS_HD void lane_emit_forces(int n, const LaneRegs<EPL> &rg, const LaneStore &ls
         stage[(long)(kk >> 1) * 2 * ls.ls + (kk & 1)] = rg.I[kk];
         if (e < n) {
             double Mc = 0.0, Qv = 0.0;
-            if (fields) element_forces<EPL>(rg, ls, gs, kk, Mc, Qv);
+            if (fields) element_forces<EPL>(rg, ls, gs, invLe, kk, Mc, Qv);
             shear[e] = fields ? (float)Qv : 0.0f;
             moment[e] = fields ? (float)(-Mc) : 0.0f;
         }

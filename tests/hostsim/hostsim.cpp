@@ -280,11 +280,11 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             for (int c = 0; c < NC; ++c) {
                 for (int l = 0; l < LPB; ++l) lane_reduce(l, fb[c].m, ls[c][l], gs[c]);
                 for (int l = LPB - 1; l >= 0; --l) rc |= group_solve(fb[c], gs[c], l);
-                if (NC > 1) for (int l = 0; l < LPB; ++l) lane_case_squares<EPL>(rg[c][l], ls[c][l], gs[c]);
+                if (NC > 1) for (int l = 0; l < LPB; ++l) lane_case_squares<EPL>(rg[c][l], ls[c][l], gs[c], fb[c].invLe);
             }
             float lv[NC][LPB];
             for (int c = 0; c < NC; ++c)
-                for (int l = 0; l < LPB; ++l) lane_forces<EPL, NC>(k, n, rg[c][l], ls[c][l], gs[c], l, c);
+                for (int l = 0; l < LPB; ++l) lane_forces<EPL, NC>(k, n, rg[c][l], ls[c][l], gs[c], fb[c].invLe, l, c);
             for (int c = 0; c < NC; ++c)
                 for (int l = 0; l < LPB; ++l) lv[c][l] = group_loss(k, n, ls[c][l], l);
             for (int c = 0; c < NC; ++c)
@@ -306,7 +306,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
         for (int c = 0; c < NC; ++c) {
             const int64_t bc = b * NC + c;
             for (int l = 0; l < LPB; ++l)
-                lane_emit_forces<EPL>(n, rg[c][l], ls[c][l], gs[c], l, fields, shear + bc * n, moment + bc * n);
+                lane_emit_forces<EPL>(n, rg[c][l], ls[c][l], gs[c], fb[c].invLe, l, fields, shear + bc * n, moment + bc * n);
             group_emit_displacements(k, fb[c], ls[c][0], gs[c], fields, defl + bc * nn, rot + bc * nn);
             for (int l = 0; l < LPB; ++l) {
                 if (t > 0) lane_adam<EPL, false>(k, rg[c][l], ls[c][l], pass1_consts(fb[c]), neg_step, bc2_sqrt);
