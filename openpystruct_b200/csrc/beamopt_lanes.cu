@@ -25,6 +25,11 @@ using namespace lanes;
 #define OPS_LANES_MAXT 320
 #endif
 constexpr int LANES_MAX_THREADS = OPS_LANES_MAXT;
+// Many-round batches of the reference's discretisation: 12 warps per SM.  An iteration of a CTA costs a fixed
+// latency plus a part that grows with the resident warps (profiles/): 48 beams per SM and round beat 40 once a
+// batch runs several full rounds (+5 % at 6 rounds), while the 10 000-beam batch (1.7 rounds of 40) is faster at 320.
+constexpr int LANES_BIG_THREADS = 384;
+constexpr int LANES_BIG_MIN_ROUNDS = 3;
 
 // synchronisation of the NC groups of a team: one warp (NC <= 4) or 8 NC / 32 whole warps (named barrier)
 template <int NC>
@@ -54,21 +59,22 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 
     double *lane_d = reinterpret_cast<double *>(smem_raw);
     double *tab_d = lane_d + (size_t)lane_doubles(EPL, NC) * T;
+    const int GS = G;
     double *grp_d = tab_d + (size_t)TAB_SLOTS * G;
-    int *grp_i = reinterpret_cast<int *>(grp_d + (size_t)GROUP_DOUBLES * G);
+    int *grp_i = reinterpret_cast<int *>(grp_d + (size_t)GROUP_DOUBLES * GS);
     LaneStore ls;
     ls.ls = T;
     ls.mq = reinterpret_cast<Pair *>(lane_d) + tid;
     ls.scr = lane_d + (size_t)2 * EPL * T + tid;
     ls.xc = reinterpret_cast<PairF *>(lane_d + (size_t)(2 * EPL + SCR_SLOTS) * T) + tid;
     GroupStore gs;
-    gs.gs = G;
+    gs.gs = GS;
     gs.tab = tab_d + (size_t)TAB_SLOTS * g;
     gs.fs.sd = grp_d + g;
-    gs.fs.stride = G;
-    gs.gd = gs.fs.sd + (size_t)FlexStore::NUM_DOUBLES * G;
+    gs.fs.stride = GS;
+    gs.gd = gs.fs.sd + (size_t)FlexStore::NUM_DOUBLES * GS;
     gs.fs.si = grp_i + g;
-    gs.gi = gs.fs.si + (size_t)FlexStore::NUM_INTS * G;
+    gs.gi = gs.fs.si + (size_t)FlexStore::NUM_INTS * GS;
     int *team_gi = gs.gi - case_id;                                // the case-0 group's ints
 
     // Work distribution: beam b belongs to CTA b mod gridDim.x, and the groups of a CTA take the CTA's
@@ -97,11 +103,11 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             } else {
                 if (case_id == 0 && l == 0) {
                     nb = (long long)blockIdx.x + (long long)gridDim.x * atomicAdd(&cta_next, 1u);
-                    team_gi[4 * G] = (int)(nb & 0xffffffffLL);
-                    team_gi[5 * G] = (int)(nb >> 32);
+                    team_gi[4 * GS] = (int)(nb & 0xffffffffLL);
+                    team_gi[5 * GS] = (int)(nb >> 32);
                 }
                 team_sync<NC>(team_mask, barrier_id);
-                nb = ((long long)team_gi[5 * G] << 32) | (unsigned int)team_gi[4 * G];
+                nb = ((long long)team_gi[5 * GS] << 32) | (unsigned int)team_gi[4 * GS];
                 team_sync<NC>(team_mask, barrier_id);
             }
             if (nb < B) {
@@ -222,7 +228,11 @@ int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_
                              (size_t)GROUP_INTS * 4;
     int groups = (int)((size_t)smem_optin / per_group);
     int T = groups * LPB / 32 * 32;
-    if (T > LANES_MAX_THREADS) T = LANES_MAX_THREADS;
+    int cap = LANES_MAX_THREADS;
+    if (num_cases == 1 && pl->nfix == 100 && LANES_BIG_THREADS > cap &&
+        B >= (int64_t)sms * (LANES_BIG_THREADS / LPB) * LANES_BIG_MIN_ROUNDS)
+        cap = LANES_BIG_THREADS;
+    if (T > cap) T = cap;
     const char *thr_env = getenv("OPS_LANES_THREADS");            // profiling knob
     if (thr_env && atoi(thr_env) >= 32 && atoi(thr_env) <= T) T = atoi(thr_env) / 32 * 32;
     const int team_threads = num_cases * LPB;                     // whole teams per CTA (and whole warps per team)
@@ -272,6 +282,8 @@ cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, con
     }
     if (pl.nfix == 100 && pl.threads == LANES_MAX_THREADS)
         return launch_instance<13, 100, 1, LANES_MAX_THREADS>(k, B, p, pl, stream);      // the reference's discretisation
+    if (pl.nfix == 100 && pl.threads == LANES_BIG_THREADS)
+        return launch_instance<13, 100, 1, LANES_BIG_THREADS>(k, B, p, pl, stream);
     if (pl.nfix == 100) return launch_instance<13, 100, 1>(k, B, p, pl, stream);
     switch (pl.epl) {
     case 4: return launch_instance<4, 0, 1>(k, B, p, pl, stream);
