@@ -362,7 +362,8 @@ def run_ours(args):
     hbm_achieved = B * BYTES_PER_BEAM / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json"))).get("dram_bytes_per_launch")
+        if args.workload == "cfg2":     # the capture is of the default workload's kernel
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
 
@@ -405,7 +406,7 @@ def run_ours(args):
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
                      "kernel": {"cfg2": "beamopt_lanes_kernel<13,100,1>", "cfg3": "beamopt_lanes_kernel<13,100,1>",
-                                "cfg4": "beamopt_lanes_kernel<13,0,8>", "cfg5": "beamopt_flex_kernel"}[args.workload],
+                                "cfg4": "beamopt_lanes_kernel<13,0,8>", "cfg5": "beamopt_wide_kernel<32>"}[args.workload],
                      "kernel_ms": kernel_ms,
                      "flop_per_beam_iteration": F64_FLOP_PER_ITER,
                      "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
