@@ -233,7 +233,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from openpystruct_b200 import _cabi, ops
-    from openpystruct_b200.distributed import gather_outputs, init_from_env
+    from openpystruct_b200.distributed import PeerDataset, gather_outputs, init_from_env
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
@@ -256,7 +256,17 @@ def run_ours(args):
     d_in = [t.to(dev) for t in h_in]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    # N > 1: every rank optimises its own beams; the dataset gather is fused into the kernel's record write
+    # (rows copied to every peer's dataset arrays over NVLink, PeerDataset) unless --gather nccl asks for the
+    # all_gather of the per-rank blocks after the kernel
+    peer = None
+    if world > 1 and args.gather == "peer" and NUM_NODES <= 169 and args.solver == 0:     # the lanes kernel's scatter
+        peer = PeerDataset(p, B * world)
+        shard = dict(zip(("fixed_uy", "force_nodes", "force_vals", "L"), d_in))
+
     def step():
+        if peer is not None:
+            return peer.optimise(shard, rank * B)
         out = ops.optimise_beams(p, *d_in)
         if world > 1:
             out = gather_outputs(out, B * world)
@@ -293,6 +303,8 @@ def run_ours(args):
 
     # kernel-only duration (no gather), for the roofline of the dominant kernel
     kev = []
+    ops.optimise_beams(p, *d_in)                 # (first call of this path in the peer mode: allocations)
+    torch.cuda.synchronize()
     for _ in range(min(args.steps, 5)):
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -391,8 +403,11 @@ def run_ours(args):
                    "beams_per_gpu": B, "num_nodes": NUM_NODES, "num_cases": WL["num_cases"], "epochs": EPOCHS,
                    "early_stop": False,
                    "fe_precision": "f64", "optimiser_precision": "f32 (torch CPU op order)",
-                   "l2": "flushed between steps (256 MiB write)", "collective": "all_gather of the dataset per "
-                   "step" if world > 1 else "none"},
+                   "l2": "flushed between steps (256 MiB write)", "collective": "none" if world == 1 else (
+                       "dataset gather fused into the kernel: every beam's record is copied to all peers' dataset "
+                       "arrays over NVLink by the thread group that finished it (CUDA IPC mappings); NCCL carries "
+                       "two 4-byte all_reduce barriers per step" if peer is not None else
+                       "NCCL all_gather of the dataset after the kernel, every step")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "path": "ops_beamopt_session_run (C ABI; pinned host buffers, H2D of the inputs + launch + D2H of the "
@@ -436,6 +451,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--beams", type=int, default=0, help="override the workload's total beam count (exploration only)")
+    ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: dataset gather fused into the kernel (stores to the peers over NVLink) or NCCL all_gather")
     ap.add_argument("--solver", type=int, default=0, help="OPS_SOLVER_* of the C ABI (exploration only; 0 = production)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -130,6 +130,41 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
                        void *d_workspace, size_t workspace_bytes, void *cuda_stream);
 
 /*
+ * The same launch with the DATASET GATHER FUSED INTO THE KERNEL'S RECORD WRITE (beams shard over the GPUs
+ * of a box with no per-iteration communication; the only exchange is the final gather of the dataset, which the
+ * reference does by appending worker results in the parent process, MultiCore:258-270).  `dests` holds n_dest
+ * (1..8) sets of the eight record arrays, each sized for the WHOLE dataset: this GPU's own FIRST, then its peers',
+ * mapped into this process with ops_peer_open.  Beam b of this launch is written to row row0 + b of set 0 and
+ * copied by the same thread group to that row of every other set (stores over NVLink) while the other beams keep
+ * iterating, so when all ranks' launches have completed every GPU holds the complete dataset; the caller orders that with a barrier on the stream (e.g. a one-element NCCL all_reduce).
+ * Production (lanes) kernel only: OPS_E_UNSUPP for configurations that run another kernel.
+ */
+typedef struct OpsBeamOptRecordArrays {
+    float *I_values;
+    double *deflections, *rotations;
+    float *shear, *moment;
+    int32_t *epochs;
+    float *loss;
+    int32_t *status;
+} OpsBeamOptRecordArrays;
+
+int ops_beamopt_launch_scatter(const OpsBeamOptParams *p, int64_t B,
+                               const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                               const double *L, const float *d_schedule,
+                               int n_dest, const OpsBeamOptRecordArrays *dests, int64_t row0,
+                               void *d_workspace, size_t workspace_bytes, void *cuda_stream);
+
+/*
+ * Peer-visible device buffers for the scatter above (CUDA IPC; one process per GPU).  ops_peer_alloc: cudaMalloc on
+ * the current device + a 64-byte handle to send to the other ranks; ops_peer_open: map a peer's buffer into this
+ * process (peer access is enabled lazily); ops_peer_close / ops_peer_free undo them.  0 / OPS_E_* / cudaError_t.
+ */
+int ops_peer_alloc(size_t bytes, void **dptr, unsigned char *handle64);
+int ops_peer_open(const unsigned char *handle64, void **dptr);
+int ops_peer_close(void *dptr);
+int ops_peer_free(void *dptr);
+
+/*
  * One static solve per beam for given inertias, everything in FP64 (no optimiser): the
  * setup_model + analyze + eleResponse + nodeDisp sequence (SingleCore:176-190, 224-232) in isolation.
  * I_f64[B][n]; single load case (force arrays [B][max_forces]); outputs f64 [B][num_nodes] / [B][n].

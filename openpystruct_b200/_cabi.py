@@ -18,6 +18,7 @@ EXPORTS = (
     "ops_fp64_peak_probe", "ops_fastmath_selftest", "ops_pipe_probe",
     "ops_beamopt_session_create", "ops_beamopt_session_arrays", "ops_beamopt_session_run",
     "ops_beamopt_session_destroy",
+    "ops_beamopt_launch_scatter", "ops_peer_alloc", "ops_peer_open", "ops_peer_close", "ops_peer_free",
 )
 
 
@@ -38,6 +39,12 @@ class OpsBeamOptParams(C.Structure):
 class OpsBeamOptHostArrays(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("fixed_uy", "force_nodes", "force_vals", "L", "I_values", "deflections",
                                           "rotations", "shear", "moment", "epochs", "loss", "status")]
+
+
+class OpsBeamOptRecordArrays(C.Structure):
+    """One set of dataset arrays (device pointers) of ops_beamopt_launch_scatter."""
+    _fields_ = [(n, C.c_void_p) for n in ("I_values", "deflections", "rotations", "shear", "moment", "epochs", "loss",
+                                          "status")]
 
 
 class CudaLibraryError(RuntimeError):
@@ -84,6 +91,12 @@ def lib():
         L.ops_beamopt_session_run.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float)]
         L.ops_beamopt_session_destroy.argtypes = [C.c_void_p]
         L.ops_beamopt_session_destroy.restype = None
+        L.ops_beamopt_launch_scatter.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 5 + \
+            [C.c_int, C.POINTER(OpsBeamOptRecordArrays), C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ops_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+        L.ops_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.ops_peer_close.argtypes = [C.c_void_p]
+        L.ops_peer_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

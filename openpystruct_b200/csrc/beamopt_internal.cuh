@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "beamopt_core.cuh"
+#include "beamopt_lanes.cuh"
 
 namespace ops {
 
@@ -25,6 +26,11 @@ struct OptPtrs {
     double *ws_d;      // global scratch (thread-per-beam kernels only)
     float *ws_f;
     uint32_t *ws_mask;
+    // Record destinations of the lanes kernel: beam b of this launch is row row0 + b of EVERY destination's arrays.
+    // One destination (row0 = 0) = the arrays above; several = the same dataset arrays of the peer GPUs, mapped
+    // into this process (ops_peer_*): the kernel's record write is the dataset gather (ops_beamopt_launch_scatter).
+    lanes::RecordDest dest;
+    long long row0;
 };
 
 // eight-lanes-per-beam three-moment kernel (beamopt_lanes.cu)
@@ -36,6 +42,7 @@ struct LanesPlan {
     size_t smem_bytes;
 };
 bool lanes_supported(const BeamConsts &k, int num_cases);
+bool lanes_scatter_supported(const LanesPlan &pl);
 int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_optin, LanesPlan *pl);
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream);
 

@@ -595,11 +595,14 @@ size_t ops_beamopt_workspace_bytes(const OpsBeamOptParams *p, int64_t B)
     return 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
 }
 
-int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
+// One launch; n_dest == 0: the record arrays given here (rows 0..B-1); n_dest >= 1: `dests` holds n_dest sets of the
+// eight record arrays (order of OpsBeamOptRecordArrays) and beam b is written to row row0 + b of every set.
+static int launch_impl(const OpsBeamOptParams *p, int64_t B,
                        const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
                        const double *L, const float *d_schedule,
                        float *I_values, double *deflections, double *rotations, float *shear,
                        float *moment, int32_t *epochs, float *loss, int32_t *status,
+                       int n_dest, const OpsBeamOptRecordArrays *dests, int64_t row0,
                        void *d_workspace, size_t workspace_bytes, void *cuda_stream)
 {
     BeamConsts k;
@@ -607,13 +610,16 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
     if (rc) return rc;
     if (B < 0) return OPS_E_BADARG;
     if (B == 0) return 0;
-    if (!fixed_uy || !L || !I_values || !deflections || !rotations || !shear || !moment || !epochs ||
-        !loss || !status || !d_workspace || (p->max_forces > 0 && (!force_nodes || !force_vals)) ||
+    if (n_dest == 0 && (!I_values || !deflections || !rotations || !shear || !moment || !epochs || !loss || !status))
+        return OPS_E_BADARG;
+    if (!fixed_uy || !L || !d_workspace || (p->max_forces > 0 && (!force_nodes || !force_vals)) ||
         (p->max_epochs > 0 && !d_schedule))
         return OPS_E_BADARG;
+    if (n_dest < 0 || n_dest > lanes::MAX_DEST || (n_dest > 0 && !dests) || row0 < 0) return OPS_E_BADARG;
     LaunchPlan pl;
     rc = plan_launch(k, p->num_cases, B, p->solver, &pl);
     if (rc) return rc;
+    if (n_dest > 1 && !(pl.lanes && lanes_scatter_supported(pl.lp))) return OPS_E_UNSUPP;   // the lanes kernel's scatter instances
     const size_t need = 256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512;
     if (workspace_bytes < need) return OPS_E_WORKSPACE;
     cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -623,6 +629,23 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
     q.fixed_uy = fixed_uy; q.force_nodes = force_nodes; q.force_vals = force_vals; q.L = L;
     q.sched = d_schedule; q.I_values = I_values; q.defl = deflections; q.rot = rotations;
     q.shear = shear; q.moment = moment; q.epochs = epochs; q.loss = loss; q.status = status;
+    memset(&q.dest, 0, sizeof(q.dest));
+    q.row0 = n_dest > 0 ? (long long)row0 : 0;
+    q.dest.nd = n_dest > 0 ? n_dest : 1;
+    for (int r = 0; r < q.dest.nd; ++r) {
+        OpsBeamOptRecordArrays a;
+        if (n_dest > 0) a = dests[r];
+        else { a.I_values = I_values; a.deflections = deflections; a.rotations = rotations; a.shear = shear;
+               a.moment = moment; a.epochs = epochs; a.loss = loss; a.status = status; }
+        if (!a.I_values || !a.deflections || !a.rotations || !a.shear || !a.moment || !a.epochs || !a.loss || !a.status)
+            return OPS_E_BADARG;
+        q.dest.I[r] = a.I_values; q.dest.defl[r] = a.deflections; q.dest.rot[r] = a.rotations;
+        q.dest.shear[r] = a.shear; q.dest.moment[r] = a.moment; q.dest.epochs[r] = a.epochs;
+        q.dest.loss[r] = a.loss; q.dest.status[r] = a.status;
+    }
+    // destination 0 is where the kernel writes the record; it copies the rows to the others
+    q.I_values = q.dest.I[0]; q.defl = q.dest.defl[0]; q.rot = q.dest.rot[0]; q.shear = q.dest.shear[0];
+    q.moment = q.dest.moment[0]; q.epochs = q.dest.epochs[0]; q.loss = q.dest.loss[0]; q.status = q.dest.status[0];
     q.counter = (unsigned long long *)ws;
     size_t off = 256;
     q.ws_d = (double *)(ws + off); off += (pl.ws_d_bytes + 255) / 256 * 256;
@@ -662,6 +685,68 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
     else         { if (mf == 4) OPS_LAUNCH(4, false); else OPS_LAUNCH(8, false); }
 #undef OPS_LAUNCH
     e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
+                       const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                       const double *L, const float *d_schedule,
+                       float *I_values, double *deflections, double *rotations, float *shear,
+                       float *moment, int32_t *epochs, float *loss, int32_t *status,
+                       void *d_workspace, size_t workspace_bytes, void *cuda_stream)
+{
+    return launch_impl(p, B, fixed_uy, force_nodes, force_vals, L, d_schedule, I_values, deflections, rotations, shear,
+                       moment, epochs, loss, status, 0, nullptr, 0, d_workspace, workspace_bytes, cuda_stream);
+}
+
+int ops_beamopt_launch_scatter(const OpsBeamOptParams *p, int64_t B,
+                               const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                               const double *L, const float *d_schedule,
+                               int n_dest, const OpsBeamOptRecordArrays *dests, int64_t row0,
+                               void *d_workspace, size_t workspace_bytes, void *cuda_stream)
+{
+    if (n_dest < 1) return OPS_E_BADARG;
+    return launch_impl(p, B, fixed_uy, force_nodes, force_vals, L, d_schedule, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, nullptr, n_dest, dests, row0, d_workspace, workspace_bytes, cuda_stream);
+}
+
+// --- peer-visible device buffers (CUDA IPC): the dataset arrays the in-kernel scatter writes over NVLink ---
+int ops_peer_alloc(size_t bytes, void **dptr, unsigned char *handle64)
+{
+    if (!dptr || !handle64 || bytes == 0) return OPS_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return (int)e;
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, d);
+    if (e != cudaSuccess) { cudaFree(d); return (int)e; }
+    memcpy(handle64, &h, 64);
+    *dptr = d;
+    return 0;
+}
+
+int ops_peer_open(const unsigned char *handle64, void **dptr)
+{
+    if (!dptr || !handle64) return OPS_E_BADARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *d = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return (int)e;
+    *dptr = d;
+    return 0;
+}
+
+int ops_peer_close(void *dptr)
+{
+    cudaError_t e = cudaIpcCloseMemHandle(dptr);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int ops_peer_free(void *dptr)
+{
+    cudaError_t e = cudaFree(dptr);
     return e == cudaSuccess ? 0 : (int)e;
 }
 

@@ -40,9 +40,12 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
     else asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "n"(NC * LPB) : "memory");
 }
 
+// SC: instance with the in-kernel dataset gather (the peers' copies of a finished beam's rows).  A separate
+// instance because the mere presence of that cold code costs the 320-thread instance 4.7 % on 10 000 beams (same
+// epoch-loop instructions, different code placement; profiles/r01_v6_ab_scatter.txt).
 // TFIX: compile-time CTA size (0 = blockDim.x).  With it every shared-memory column stride is an immediate
 // and the [slot][thread] addressing costs no integer instructions.
-template <int EPL, int NFIX, int NC, int TFIX>
+template <int EPL, int NFIX, int NC, int TFIX, bool SC>
 __global__ void __launch_bounds__(TFIX ? TFIX : LANES_MAX_THREADS, 1)
 beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 {
@@ -184,20 +187,24 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             } else {
                 // record of the beam: fields of the last analysed inertias, then the last Adam step
                 const bool fields = (t > 0) && (bad == 0);
-                const long long bc = b * NC + case_id;
-                lane_emit_forces<EPL>(n, rg, ls, gs, fb.invLe, l, fields, p.shear + bc * n, p.moment + bc * n);
+                const long long row = p.row0 + b, rowc = row * NC + case_id;      // dataset rows of the beam / its load case
+                lane_emit_forces<EPL>(n, rg, ls, gs, fb.invLe, l, fields, p.shear + rowc * n, p.moment + rowc * n);
                 __syncwarp(gmask);
                 if (l == 0) {
                     LaneStore ls0 = ls;
-                    group_emit_displacements(k, fb, ls0, gs, fields, p.defl + bc * nn, p.rot + bc * nn);
+                    group_emit_displacements(k, fb, ls0, gs, fields, p.defl + rowc * nn, p.rot + rowc * nn);
                     if (case_id == 0) {
-                        p.epochs[b] = t;
-                        p.loss[b] = lossf;
-                        p.status[b] = bad;
+                        p.epochs[row] = t;
+                        p.loss[row] = lossf;
+                        p.status[row] = bad;
                     }
                 }
                 if (t > 0) lane_adam<EPL, false>(k, rg, ls, pc, neg_step, bc2_sqrt);
-                if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + b * n);
+                if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + row * n);
+                if (SC && p.dest.nd > 1) {                                     // dataset gather: the peers' copies of the rows
+                    __syncwarp(gmask);
+                    lane_copy_record(n, nn, l, p.dest, row, rowc, case_id == 0);
+                }
                 __syncwarp(gmask);
                 have = false;
             }
@@ -252,45 +259,57 @@ int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_
     return 0;
 }
 
-template <int EPL, int NFIX, int NC, int TFIX = 0>
+template <int EPL, int NFIX, int NC, int TFIX = 0, bool SC = false>
 static cudaError_t launch_instance(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl,
                                    cudaStream_t stream)
 {
-    auto kern = beamopt_lanes_kernel<EPL, NFIX, NC, TFIX>;
+    auto kern = beamopt_lanes_kernel<EPL, NFIX, NC, TFIX, SC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<pl.blocks, pl.threads, pl.smem_bytes, stream>>>(k, B, p);
     return cudaGetLastError();
 }
 
+// instances with the in-kernel dataset gather: every single-case instance, and the 13-slot multi-case ones
+bool lanes_scatter_supported(const LanesPlan &pl) { return pl.num_cases == 1 || pl.epl == 13; }
+
+template <bool SC>
+static cudaError_t launch_single_case(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl,
+                                      cudaStream_t stream)
+{
+    if (pl.nfix == 100 && pl.threads == LANES_MAX_THREADS)
+        return launch_instance<13, 100, 1, LANES_MAX_THREADS, SC>(k, B, p, pl, stream);  // the reference's discretisation
+    if (pl.nfix == 100 && pl.threads == LANES_BIG_THREADS)
+        return launch_instance<13, 100, 1, LANES_BIG_THREADS, SC>(k, B, p, pl, stream);
+    if (pl.nfix == 100) return launch_instance<13, 100, 1, 0, SC>(k, B, p, pl, stream);
+    switch (pl.epl) {
+    case 4: return launch_instance<4, 0, 1, 0, SC>(k, B, p, pl, stream);
+    case 8: return launch_instance<8, 0, 1, 0, SC>(k, B, p, pl, stream);
+    case 13: return launch_instance<13, 0, 1, 0, SC>(k, B, p, pl, stream);
+    default: return launch_instance<21, 0, 1, 0, SC>(k, B, p, pl, stream);
+    }
+}
+
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream)
 {
+    const bool sc = p.dest.nd > 1;
+    if (sc && !lanes_scatter_supported(pl)) return cudaErrorInvalidValue;
     if (pl.num_cases > 1) {
         // load cases sharing one inertia vector: the 100-element discretisation and the generic <= 104-element one
         switch (pl.num_cases * 100 + pl.epl) {
         case 204: return launch_instance<4, 0, 2>(k, B, p, pl, stream);
         case 208: return launch_instance<8, 0, 2>(k, B, p, pl, stream);
-        case 213: return launch_instance<13, 0, 2>(k, B, p, pl, stream);
+        case 213: return sc ? launch_instance<13, 0, 2, 0, true>(k, B, p, pl, stream) : launch_instance<13, 0, 2>(k, B, p, pl, stream);
         case 404: return launch_instance<4, 0, 4>(k, B, p, pl, stream);
         case 408: return launch_instance<8, 0, 4>(k, B, p, pl, stream);
-        case 413: return launch_instance<13, 0, 4>(k, B, p, pl, stream);
+        case 413: return sc ? launch_instance<13, 0, 4, 0, true>(k, B, p, pl, stream) : launch_instance<13, 0, 4>(k, B, p, pl, stream);
         case 804: return launch_instance<4, 0, 8>(k, B, p, pl, stream);
         case 808: return launch_instance<8, 0, 8>(k, B, p, pl, stream);
-        case 813: return launch_instance<13, 0, 8>(k, B, p, pl, stream);
+        case 813: return sc ? launch_instance<13, 0, 8, 0, true>(k, B, p, pl, stream) : launch_instance<13, 0, 8>(k, B, p, pl, stream);
         default: return cudaErrorInvalidValue;
         }
     }
-    if (pl.nfix == 100 && pl.threads == LANES_MAX_THREADS)
-        return launch_instance<13, 100, 1, LANES_MAX_THREADS>(k, B, p, pl, stream);      // the reference's discretisation
-    if (pl.nfix == 100 && pl.threads == LANES_BIG_THREADS)
-        return launch_instance<13, 100, 1, LANES_BIG_THREADS>(k, B, p, pl, stream);
-    if (pl.nfix == 100) return launch_instance<13, 100, 1>(k, B, p, pl, stream);
-    switch (pl.epl) {
-    case 4: return launch_instance<4, 0, 1>(k, B, p, pl, stream);
-    case 8: return launch_instance<8, 0, 1>(k, B, p, pl, stream);
-    case 13: return launch_instance<13, 0, 1>(k, B, p, pl, stream);
-    default: return launch_instance<21, 0, 1>(k, B, p, pl, stream);
-    }
+    return sc ? launch_single_case<true>(k, B, p, pl, stream) : launch_single_case<false>(k, B, p, pl, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

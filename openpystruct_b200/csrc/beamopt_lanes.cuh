@@ -68,6 +68,19 @@ struct alignas(16) Pair {                       // two doubles moved with one 12
     double x, y;
 };
 
+// Where a beam's record goes: the same row of up to MAX_DEST sets of dataset arrays (this GPU's and, for the
+// in-kernel dataset gather, its peers' over NVLink).  Layouts: include/openpystruct_b200.h, ops_beamopt_launch.
+constexpr int MAX_DEST = 8;
+struct RecordDest {
+    int nd;
+    float *I[MAX_DEST];
+    double *defl[MAX_DEST], *rot[MAX_DEST];
+    float *shear[MAX_DEST], *moment[MAX_DEST];
+    int *epochs[MAX_DEST];
+    float *loss[MAX_DEST];
+    int *status[MAX_DEST];
+};
+
 // per-lane shared columns, entry k at base[k * ls]
 struct alignas(8) PairF {                       // {M^2, V^2} of one load case, fp32
     float c, h;
@@ -647,6 +660,30 @@ OPS_HD void lane_emit_inertias(int n, const LaneRegs<EPL> &rg, int l, float *I_o
     for (int kk = 0; kk < EPL; ++kk) {
         const int e = LPB * kk + l;
         if (e < n) I_out[e] = rg.I[kk];
+    }
+}
+
+// In-kernel dataset gather: the group copies the record it has just written (destination 0 = this GPU's dataset
+// arrays) into the same rows of the other destinations, the peers' arrays over NVLink, eight lanes wide.  Each
+// lane re-reads its own elements of I / shear / moment; deflections and rotations were written by lane 0, so the
+// caller puts a group barrier in front.
+OPS_HD void lane_copy_record(int n, int nn, int l, const RecordDest &dst, long long row, long long rowc, bool first_case)
+{
+    for (int r = 1; r < dst.nd; ++r) {
+        for (int i = l; i < n; i += LPB) {
+            dst.shear[r][rowc * n + i] = dst.shear[0][rowc * n + i];
+            dst.moment[r][rowc * n + i] = dst.moment[0][rowc * n + i];
+            if (first_case) dst.I[r][row * n + i] = dst.I[0][row * n + i];
+        }
+        for (int i = l; i < nn; i += LPB) {
+            dst.defl[r][rowc * nn + i] = dst.defl[0][rowc * nn + i];
+            dst.rot[r][rowc * nn + i] = dst.rot[0][rowc * nn + i];
+        }
+        if (first_case && l == 0) {
+            dst.epochs[r][row] = dst.epochs[0][row];
+            dst.loss[r][row] = dst.loss[0][row];
+            dst.status[r][row] = dst.status[0][row];
+        }
     }
 }
 

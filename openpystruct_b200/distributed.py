@@ -6,6 +6,11 @@ reference's serial loop, SingleCore:256-257, which the trainers' consecutive-rec
 on, PINN:237-258) and one ``all_gather_into_tensor`` per output tensor (NCCL over NVLink on GPUs)
 reassembles the dataset.  Results are independent of the world size bit for bit.
 
+On one NVLink box the gather can be fused into the kernel instead (``PeerDataset``): every rank maps
+every other rank's dataset arrays (CUDA IPC) and the production kernel writes each finished beam's
+record straight into all of them, so the transfer overlaps the optimisation of the beams still
+running and NCCL only carries a 4-byte all_reduce as the closing barrier.
+
 The reference has no counterpart (its parallelism is joblib/loky processes, MultiCore:258).
 """
 from __future__ import annotations
@@ -108,6 +113,140 @@ def optimise_beams_sharded(params, inputs: Dict[str, torch.Tensor], group=None, 
         return _ops.optimise_beams(params, shard["fixed_uy"], shard["force_nodes"], shard["force_vals"],
                                    shard["L"])
     return run_sharded(compute, inputs, group, gather)
+
+
+class PeerDataset:
+    """The whole dataset's record arrays on THIS GPU, writable by every rank's kernel over NVLink.
+
+    ``PeerDataset(params, num_beams, group)`` is collective: each rank allocates one device buffer
+    (``ops_peer_alloc``), the 64-byte IPC handles are exchanged through ``torch.distributed`` and every
+    rank maps the others' buffers (``ops_peer_open``).  ``optimise(shard_inputs, row0)`` launches the
+    production kernel on this rank's beams with all ``world`` buffers as destinations and closes with a
+    one-element all_reduce on the stream: when it has run, ``tensors()`` holds the complete dataset on
+    every rank.  The tensors alias the peer buffer -- consume or clone them before any rank's next call.
+    """
+
+    NAMES = OUTPUT_NAMES
+
+    def __init__(self, params, num_beams: int, group=None, device: Optional[torch.device] = None):
+        import ctypes as C
+        from . import _cabi
+        self._cabi, self._C = _cabi, C
+        self.params, self.num_beams, self.group = params, int(num_beams), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("PeerDataset: at most 8 ranks (one NVLink box)")
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        nn, Cc = params.num_nodes, params.num_cases
+        n, Bt = nn - 1, self.num_beams
+        spec = (("I", (Bt, n), torch.float32), ("defl", (Bt, Cc, nn), torch.float64), ("rot", (Bt, Cc, nn), torch.float64),
+                ("shear", (Bt, Cc, n), torch.float32), ("moment", (Bt, Cc, n), torch.float32),
+                ("epochs", (Bt,), torch.int32), ("loss", (Bt,), torch.float32), ("status", (Bt,), torch.int32))
+        self._layout, off = [], 0
+        for name, shape, dtype in spec:
+            nbytes = int(torch.empty((), dtype=dtype).element_size())
+            for d in shape:
+                nbytes *= d
+            self._layout.append((name, off, shape, dtype))
+            off += (nbytes + 255) // 256 * 256
+        self.nbytes = max(off, 256)
+        lib = _cabi.lib()
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.ops_set_device(self.device.index), "ops_set_device")
+            base = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            _cabi.check(lib.ops_peer_alloc(self.nbytes, C.byref(base), handle), "ops_peer_alloc")
+            self._own = int(base.value)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._bases = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self._bases.append(self._own)
+                    continue
+                ptr = C.c_void_p()
+                _cabi.check(lib.ops_peer_open(C.create_string_buffer(h, 64), C.byref(ptr)), f"ops_peer_open(rank {r})")
+                self._bases.append(int(ptr.value))
+        # destination 0 = this GPU's own arrays (the kernel writes the record there and copies the rows to the
+        # others); the peers follow in ring order so that the ranks do not all store to the same GPU at once
+        self._dests = (_cabi.OpsBeamOptRecordArrays * self.world)()
+        fields = ("I_values", "deflections", "rotations", "shear", "moment", "epochs", "loss", "status")
+        for i in range(self.world):
+            b = self._bases[(self.rank + i) % self.world]
+            for f, (_, o, _, _) in zip(fields, self._layout):
+                setattr(self._dests[i], f, b + o)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._tensors = {name: self._wrap(self._own + o, shape, dtype) for name, o, shape, dtype in self._layout}
+
+    def _wrap(self, ptr: int, shape, dtype) -> torch.Tensor:
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                        "strides": None}
+        if 0 in shape:
+            return torch.empty(shape, dtype=dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_Arr(), device=self.device)
+
+    def tensors(self) -> Dict[str, torch.Tensor]:
+        return dict(self._tensors)
+
+    def optimise(self, shard: Dict[str, torch.Tensor], row0: int) -> Dict[str, torch.Tensor]:
+        """Optimise this rank's beams (``shard``: fixed_uy, force_nodes, force_vals, L on this device) into rows
+        ``row0 ...`` of every rank's dataset, then the stream barrier."""
+        from . import ops as _ops
+        C, _cabi, p = self._C, self._cabi, self.params
+        B = int(shard["L"].shape[0])
+        if row0 < 0 or row0 + B > self.num_beams:
+            raise ValueError("PeerDataset.optimise: rows outside the dataset")
+        ip, fp = _ops.pack_params(p)
+        cp = _ops._c_params(ip, fp)
+        sched = _ops.device_schedule(p, self.device)
+        _ops._check_cuda(shard["fixed_uy"], shard["force_nodes"], shard["force_vals"], shard["L"], sched)
+        lib = _cabi.lib()
+        with torch.cuda.device(self.device):
+            # no rank may still be inside the kernels of its previous call when rows are rewritten
+            dist.all_reduce(self._flag, group=self.group)
+            if B > 0:
+                ws_bytes = lib.ops_beamopt_workspace_bytes(C.byref(cp), B)
+                ws = torch.empty((max(int(ws_bytes), 1),), dtype=torch.uint8, device=self.device)
+                stream = torch.cuda.current_stream(self.device)
+                rc = lib.ops_beamopt_launch_scatter(
+                    C.byref(cp), B, shard["fixed_uy"].data_ptr(), shard["force_nodes"].data_ptr(),
+                    shard["force_vals"].data_ptr(), shard["L"].data_ptr(), sched.data_ptr(),
+                    self.world, self._dests, int(row0), ws.data_ptr(), ws.numel(), stream.cuda_stream)
+                _cabi.check(rc, "ops_beamopt_launch_scatter")
+                ws.record_stream(stream)
+            dist.all_reduce(self._flag, group=self.group)      # every rank's kernel, hence every record, has landed
+        return self.tensors()
+
+    def close(self):
+        if getattr(self, "_bases", None) is None:
+            return
+        lib = self._cabi.lib()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.device):
+            for r, b in enumerate(self._bases):
+                if r != self.rank:
+                    lib.ops_peer_close(b)
+            dist.barrier(group=self.group)
+            lib.ops_peer_free(self._own)
+        self._bases, self._tensors = None, {}
+
+
+def optimise_beams_scattered(params, inputs: Dict[str, torch.Tensor], dataset: Optional[PeerDataset] = None,
+                             group=None) -> Tuple[Dict[str, torch.Tensor], PeerDataset]:
+    """``optimise_beams_sharded`` with the gather fused into the kernel.  ``inputs``: the GLOBAL beam-major
+    tensors on this rank's device; returns (dataset tensors on this rank, the PeerDataset to reuse / close)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    B = next(iter(inputs.values())).shape[0]
+    start, stop, _per = shard_bounds(B, rank, world)
+    shard = {k: t[start:stop].contiguous() for k, t in inputs.items()}
+    if dataset is None:
+        dataset = PeerDataset(params, B, group, shard["L"].device)
+    return dataset.optimise(shard, start), dataset
 
 
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:

@@ -1,0 +1,54 @@
+"""Two or more GPUs of one box (not part of the single-GPU pytest run): the in-kernel dataset gather
+(PeerDataset, ops_beamopt_launch_scatter) must produce, on EVERY rank, exactly the dataset the NCCL
+all_gather of the per-rank blocks produces.  Launch:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from openpystruct_b200 import sampling                                   # noqa: E402
+from openpystruct_b200.distributed import (PeerDataset, init_from_env, optimise_beams_scattered,   # noqa: E402
+                                            optimise_beams_sharded)
+from openpystruct_b200.params import BeamOptParams                       # noqa: E402
+from tests.helpers import seeded_cases                                   # noqa: E402
+
+
+def main():
+    rank, local, world = init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    for script, count, cases_per_beam in (("MC", 3001, 1), ("SC", 777, 1), ("MC", 402, 4)):
+        p = BeamOptParams.for_script(script)
+        if cases_per_beam > 1:
+            p = p.replace(num_cases=cases_per_beam)
+        cases = seeded_cases(p, count * cases_per_beam, seed=17)
+        fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases, cases_per_beam)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+        inputs = {"fixed_uy": t(fixed), "force_nodes": t(fn), "force_vals": t(fv), "L": t(L)}
+        want = optimise_beams_sharded(p, inputs)
+        got, ds = optimise_beams_scattered(p, inputs)
+        torch.cuda.synchronize()
+        for k in want:
+            assert torch.equal(want[k], got[k][:count]), (rank, script, k)
+        # a second call reuses the mappings (rows are rewritten)
+        got2, _ = optimise_beams_scattered(p, inputs, ds)
+        torch.cuda.synchronize()
+        for k in want:
+            assert torch.equal(want[k], got2[k][:count]), (rank, script, k, "second call")
+        ds.close()
+        if rank == 0:
+            print(f"multi_gpu_check ok: {script} x{cases_per_beam} {count} beams on {world} GPUs, "
+                  f"epochs {int(want['epochs'].min())}..{int(want['epochs'].max())}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

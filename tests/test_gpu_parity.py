@@ -243,6 +243,27 @@ def test_full_size_properties_10k_beams(solver):
     assert_matches_oracle(o, {k: v[sl] for k, v in a.items()})
 
 
+def test_many_round_batches_use_the_larger_cta_and_agree_bitwise(monkeypatch):
+    """Batches of three or more full rounds run the 384-thread instance of the lanes kernel (48 beams
+    per SM and round); a beam's arithmetic does not depend on the CTA it runs in, so the record equals
+    the 320-thread instance's bit for bit.  A slice is checked against the oracle as well."""
+    p = BeamOptParams.for_script("MC")
+    B = 148 * 48 * 3 + 77
+    cases = seeded_cases(p, B, seed=311)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    monkeypatch.delenv("OPS_LANES_THREADS", raising=False)
+    a = gpu_run(p, fixed, fn, fv, L)
+    monkeypatch.setenv("OPS_LANES_THREADS", "320")
+    b = gpu_run(p, fixed, fn, fv, L)
+    monkeypatch.delenv("OPS_LANES_THREADS", raising=False)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert not a["status"].any()
+    sl = slice(B - 200, B)
+    o = oracle_run(p, fixed[sl], fn[sl], fv[sl], L[sl])
+    assert_matches_oracle(o, {k: v[sl] for k, v in a.items()})
+
+
 def test_generate_samples_batched_is_a_drop_in():
     """Same entry point, arguments and record schema as the reference's generate_sample."""
     rollers, avail = sampling.fixed_bridge(101)
