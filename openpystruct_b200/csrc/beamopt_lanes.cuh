@@ -664,25 +664,48 @@ OPS_HD void lane_emit_inertias(int n, const LaneRegs<EPL> &rg, int l, float *I_o
 }
 
 // In-kernel dataset gather: the group copies the record it has just written (destination 0 = this GPU's dataset
-// arrays) into the same rows of the other destinations, the peers' arrays over NVLink, eight lanes wide.  Each
-// lane re-reads its own elements of I / shear / moment; deflections and rotations were written by lane 0, so the
-// caller puts a group barrier in front.
+// arrays) into the same rows of the other destinations, the peers' arrays over NVLink, eight lanes wide: 16-byte
+// units (128 contiguous bytes per group and step) where the row is 16-byte aligned, 8- or 4-byte units otherwise.
+// Deflections and rotations were written by lane 0 and the other rows by all lanes, so the caller puts a group
+// barrier in front.
+struct alignas(16) Bytes16 {
+    unsigned long long a, b;
+};
+OPS_HD void lane_copy_bytes(void *dst, const void *src, long bytes, int l)
+{
+    const bool al16 = ((((unsigned long long)dst) | ((unsigned long long)src)) & 15ull) == 0;
+    const bool al8 = ((((unsigned long long)dst) | ((unsigned long long)src)) & 7ull) == 0;
+    long done = 0;
+    if (al16) {
+        const long n16 = bytes >> 4;
+        for (long i = l; i < n16; i += LPB) reinterpret_cast<Bytes16 *>(dst)[i] = reinterpret_cast<const Bytes16 *>(src)[i];
+        done = n16 << 4;
+    } else if (al8) {
+        const long n8 = bytes >> 3;
+        for (long i = l; i < n8; i += LPB)
+            reinterpret_cast<unsigned long long *>(dst)[i] = reinterpret_cast<const unsigned long long *>(src)[i];
+        done = n8 << 3;
+    }
+    const long n4 = (bytes - done) >> 2;                    // every row is a multiple of 4 bytes
+    for (long i = l; i < n4; i += LPB)
+        reinterpret_cast<unsigned int *>(static_cast<char *>(dst) + done)[i] =
+            reinterpret_cast<const unsigned int *>(static_cast<const char *>(src) + done)[i];
+}
+
 OPS_HD void lane_copy_record(int n, int nn, int l, const RecordDest &dst, long long row, long long rowc, bool first_case)
 {
     for (int r = 1; r < dst.nd; ++r) {
-        for (int i = l; i < n; i += LPB) {
-            dst.shear[r][rowc * n + i] = dst.shear[0][rowc * n + i];
-            dst.moment[r][rowc * n + i] = dst.moment[0][rowc * n + i];
-            if (first_case) dst.I[r][row * n + i] = dst.I[0][row * n + i];
-        }
-        for (int i = l; i < nn; i += LPB) {
-            dst.defl[r][rowc * nn + i] = dst.defl[0][rowc * nn + i];
-            dst.rot[r][rowc * nn + i] = dst.rot[0][rowc * nn + i];
-        }
-        if (first_case && l == 0) {
-            dst.epochs[r][row] = dst.epochs[0][row];
-            dst.loss[r][row] = dst.loss[0][row];
-            dst.status[r][row] = dst.status[0][row];
+        lane_copy_bytes(dst.shear[r] + rowc * n, dst.shear[0] + rowc * n, 4L * n, l);
+        lane_copy_bytes(dst.moment[r] + rowc * n, dst.moment[0] + rowc * n, 4L * n, l);
+        lane_copy_bytes(dst.defl[r] + rowc * nn, dst.defl[0] + rowc * nn, 8L * nn, l);
+        lane_copy_bytes(dst.rot[r] + rowc * nn, dst.rot[0] + rowc * nn, 8L * nn, l);
+        if (first_case) {
+            lane_copy_bytes(dst.I[r] + row * n, dst.I[0] + row * n, 4L * n, l);
+            if (l == 0) {
+                dst.epochs[r][row] = dst.epochs[0][row];
+                dst.loss[r][row] = dst.loss[0][row];
+                dst.status[r][row] = dst.status[0][row];
+            }
         }
     }
 }
