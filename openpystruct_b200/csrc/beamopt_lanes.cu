@@ -40,6 +40,33 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
     else asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "n"(NC * LPB) : "memory");
 }
 
+// Record of a beam (once per beam): fields of the last analysed inertias, then the last Adam step; SC instances then
+// copy the rows to the peers.  A macro because the kernel places it at two different points of the source (see the
+// note on code placement at the end of the kernel) and a lambda changes the code of the epoch loop.
+#define OPS_RECORD_PATH                                                                                              \
+    {                                                                                                                \
+        const bool fields = (t > 0) && (bad == 0);                                                                   \
+        const long long row = p.row0 + b, rowc = row * NC + case_id; /* dataset rows of the beam / its load case */  \
+        lane_emit_forces<EPL>(n, rg, ls, gs, fb.invLe, l, fields, p.shear + rowc * n, p.moment + rowc * n);          \
+        __syncwarp(gmask);                                                                                           \
+        if (l == 0) {                                                                                                \
+            LaneStore ls0 = ls;                                                                                      \
+            group_emit_displacements(k, fb, ls0, gs, fields, p.defl + rowc * nn, p.rot + rowc * nn);                 \
+            if (case_id == 0) {                                                                                      \
+                p.epochs[row] = t;                                                                                   \
+                p.loss[row] = lossf;                                                                                 \
+                p.status[row] = bad;                                                                                 \
+            }                                                                                                        \
+        }                                                                                                            \
+        if (t > 0) lane_adam<EPL, false>(k, rg, ls, pc, neg_step, bc2_sqrt);                                         \
+        if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + row * n);                                   \
+        if (SC && p.dest.nd > 1) { /* dataset gather: every lane re-reads rows other lanes wrote */                  \
+            __syncwarp(gmask);                                                                                       \
+            lane_copy_record(n, nn, l, p.dest, row, rowc, case_id == 0);                                             \
+        }                                                                                                            \
+        __syncwarp(gmask);                                                                                           \
+        have = false;                                                                                                \
+    }
 // SC: instance with the in-kernel dataset gather (the peers' copies of a finished beam's rows).  A separate
 // instance because the mere presence of that cold code costs the 320-thread instance 4.7 % on 10 000 beams (same
 // epoch-loop instructions, different code placement; profiles/r01_v6_ab_scatter.txt).
@@ -187,39 +214,21 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
         // scatter instances; the 320-thread instance that runs 10 000 beams in 1.7 rounds is 4 % faster with the
         // record path between the loss and the Adam step.
         constexpr bool ADAM_FIRST = SC || TFIX == LANES_BIG_THREADS;
-        auto record = [&]() {
-            // record of the beam: fields of the last analysed inertias, then the last Adam step
-            const bool fields = (t > 0) && (bad == 0);
-            const long long row = p.row0 + b, rowc = row * NC + case_id;      // dataset rows of the beam / its load case
-            lane_emit_forces<EPL>(n, rg, ls, gs, fb.invLe, l, fields, p.shear + rowc * n, p.moment + rowc * n);
-            __syncwarp(gmask);
-            if (l == 0) {
-                LaneStore ls0 = ls;
-                group_emit_displacements(k, fb, ls0, gs, fields, p.defl + rowc * nn, p.rot + rowc * nn);
-                if (case_id == 0) {
-                    p.epochs[row] = t;
-                    p.loss[row] = lossf;
-                    p.status[row] = bad;
-                }
-            }
-            if (t > 0) lane_adam<EPL, false>(k, rg, ls, pc, neg_step, bc2_sqrt);
-            if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + row * n);
-            if (SC && p.dest.nd > 1) {                                     // dataset gather: the peers' copies of the rows
-                __syncwarp(gmask);                                         // (every lane re-reads rows other lanes wrote)
-                lane_copy_record(n, nn, l, p.dest, row, rowc, case_id == 0);
-            }
-            __syncwarp(gmask);
-            have = false;
-        };
         if (ADAM_FIRST) {
             if (have && !done) lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
-            if (have && done) record();
+            if (have && done) {
+                OPS_RECORD_PATH
+            }
         } else if (have) {
-            if (!done) lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);
-            else record();
+            if (!done) {
+                lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);
+            } else {
+                OPS_RECORD_PATH
+            }
         }
     }
 }
+#undef OPS_RECORD_PATH
 
 bool lanes_supported(const BeamConsts &k, int num_cases)
 {
