@@ -252,7 +252,10 @@ beamopt_wide_kernel(const BeamConsts k, const long long B, const OptPtrs p, cons
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-constexpr int WIDE8_MAXT = 512, WIDE32_MAXT = 512;
+#ifndef OPS_WIDE32_MAXT
+#define OPS_WIDE32_MAXT 512
+#endif
+constexpr int WIDE8_MAXT = 512, WIDE32_MAXT = OPS_WIDE32_MAXT;
 
 bool wide_supported(const BeamConsts &k, int num_cases, int lpb, int smem_optin)
 {

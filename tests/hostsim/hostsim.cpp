@@ -318,6 +318,26 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
     return 0;
 }
 
+// The peers' copies of one beam's rows (lane_copy_record, the in-kernel dataset gather) run lane by lane on two
+// host "GPUs": dest[0] holds the record, dest[1] receives it.  Arrays are caller-owned, whole-dataset sized.
+extern "C" int hostsim_copy_record(int n, int nn, int64_t row, int64_t rowc, int first_case,
+                                   float *I0, double *defl0, double *rot0, float *shear0, float *moment0,
+                                   int32_t *epochs0, float *loss0, int32_t *status0,
+                                   float *I1, double *defl1, double *rot1, float *shear1, float *moment1,
+                                   int32_t *epochs1, float *loss1, int32_t *status1)
+{
+    using namespace ops::lanes;
+    RecordDest d;
+    memset(&d, 0, sizeof(d));
+    d.nd = 2;
+    d.I[0] = I0; d.defl[0] = defl0; d.rot[0] = rot0; d.shear[0] = shear0; d.moment[0] = moment0;
+    d.epochs[0] = epochs0; d.loss[0] = loss0; d.status[0] = status0;
+    d.I[1] = I1; d.defl[1] = defl1; d.rot[1] = rot1; d.shear[1] = shear1; d.moment[1] = moment1;
+    d.epochs[1] = epochs1; d.loss[1] = loss1; d.status[1] = status1;
+    for (int l = 0; l < LPB; ++l) lane_copy_record(n, nn, l, d, row, rowc, first_case != 0);
+    return 0;
+}
+
 extern "C" int hostsim_beamopt_lanes(const OpsBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
                                      const int32_t *force_nodes, const double *force_vals, const double *L,
                                      const float *sched, float *I_values, double *defl, double *rot,

@@ -180,3 +180,34 @@ def test_other_discretisations_against_c_oracle(num_nodes, solver):
     assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
     assert (a["loss"] == b["loss"]).mean() > 0.95
     assert rel_err(b["moment"][:, 0], a["moment"][:, 0]).max() < 1e-6
+
+
+@pytest.mark.parametrize("num_nodes,num_cases", [(101, 1), (101, 4), (34, 1), (88, 2)])
+def test_peer_copy_of_a_record_moves_exactly_its_rows(num_nodes, num_cases):
+    """lane_copy_record (the in-kernel dataset gather): the eight lanes copy one beam's rows of all record arrays
+    into the second destination -- whatever the alignment of the row (16-, 8- and 4-byte units) -- and nothing else."""
+    import ctypes as C
+    from tests.helpers import hostsim_lib
+    hs = hostsim_lib()
+    rng = np.random.default_rng(5)
+    nn, n, B = num_nodes, num_nodes - 1, 7
+    shapes = {"I": ((B, n), np.float32), "defl": ((B, num_cases, nn), np.float64), "rot": ((B, num_cases, nn), np.float64),
+              "shear": ((B, num_cases, n), np.float32), "moment": ((B, num_cases, n), np.float32),
+              "epochs": ((B,), np.int32), "loss": ((B,), np.float32), "status": ((B,), np.int32)}
+    src = {k: (rng.standard_normal(sh) * 100).astype(dt) for k, (sh, dt) in shapes.items()}
+    dst = {k: np.full(sh, -7, dt) for k, (sh, dt) in shapes.items()}
+    want = {k: v.copy() for k, v in dst.items()}
+    order = ("I", "defl", "rot", "shear", "moment", "epochs", "loss", "status")
+    for row in (0, 3, 6):
+        for c in range(num_cases):
+            rowc = row * num_cases + c
+            rc = hs.hostsim_copy_record(n, nn, C.c_int64(row), C.c_int64(rowc), int(c == 0),
+                                        *[C.c_void_p(src[k].ctypes.data) for k in order],
+                                        *[C.c_void_p(dst[k].ctypes.data) for k in order])
+            assert rc == 0
+            for k in ("defl", "rot", "shear", "moment"):
+                want[k][row, c] = src[k][row, c]
+        for k in ("I", "epochs", "loss", "status"):
+            want[k][row] = src[k][row]
+    for k in order:
+        assert np.array_equal(want[k], dst[k]), k
