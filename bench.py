@@ -233,7 +233,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from openpystruct_b200 import _cabi, ops
-    from openpystruct_b200.distributed import PeerDataset, gather_outputs, init_from_env
+    from openpystruct_b200.distributed import PeerDataset, PeerUnavailable, gather_outputs, init_from_env
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
@@ -261,8 +261,12 @@ def run_ours(args):
     # all_gather of the per-rank blocks after the kernel
     peer = None
     if world > 1 and args.gather == "peer" and NUM_NODES <= 169 and args.solver == 0:     # the lanes kernel's scatter
-        peer = PeerDataset(p, B * world)
-        shard = dict(zip(("fixed_uy", "force_nodes", "force_vals", "L"), d_in))
+        try:
+            peer = PeerDataset(p, B * world)
+            shard = dict(zip(("fixed_uy", "force_nodes", "force_vals", "L"), d_in))
+        except PeerUnavailable as ex:                 # agreed on by all ranks: NCCL gather instead
+            if rank == 0:
+                print(f"bench.py: {ex}; using the NCCL gather", file=sys.stderr, flush=True)
 
     def step():
         if peer is not None:

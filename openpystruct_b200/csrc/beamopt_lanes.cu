@@ -213,7 +213,10 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
         // 48 KB range -- best for many-round batches (384-thread instance, +2.6 % on 1 M beams) and no worse for the
         // scatter instances; the 320-thread instance that runs 10 000 beams in 1.7 rounds is 4 % faster with the
         // record path between the loss and the Adam step.
-        constexpr bool ADAM_FIRST = SC || TFIX == LANES_BIG_THREADS;
+#ifndef OPS_ADAM_FIRST_SC
+#define OPS_ADAM_FIRST_SC 1
+#endif
+        constexpr bool ADAM_FIRST = (SC && OPS_ADAM_FIRST_SC) || TFIX == LANES_BIG_THREADS;
         if (ADAM_FIRST) {
             if (have && !done) lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
             if (have && done) {

@@ -115,6 +115,10 @@ def optimise_beams_sharded(params, inputs: Dict[str, torch.Tensor], group=None, 
     return run_sharded(compute, inputs, group, gather)
 
 
+class PeerUnavailable(RuntimeError):
+    """CUDA IPC / peer access between the ranks' GPUs does not work here (raised on every rank alike)."""
+
+
 class PeerDataset:
     """The whole dataset's record arrays on THIS GPU, writable by every rank's kernel over NVLink.
 
@@ -151,22 +155,44 @@ class PeerDataset:
             off += (nbytes + 255) // 256 * 256
         self.nbytes = max(off, 256)
         lib = _cabi.lib()
+        # Collective set-up that cannot leave a rank behind: every rank takes part in every exchange whatever
+        # happened locally, and the outcome is agreed on with an all_reduce (PeerUnavailable on ALL ranks).
+        err, self._own, self._bases = None, 0, []
         with torch.cuda.device(self.device):
-            _cabi.check(lib.ops_set_device(self.device.index), "ops_set_device")
-            base = C.c_void_p()
             handle = C.create_string_buffer(64)
-            _cabi.check(lib.ops_peer_alloc(self.nbytes, C.byref(base), handle), "ops_peer_alloc")
-            self._own = int(base.value)
+            try:
+                _cabi.check(lib.ops_set_device(self.device.index), "ops_set_device")
+                base = C.c_void_p()
+                _cabi.check(lib.ops_peer_alloc(self.nbytes, C.byref(base), handle), "ops_peer_alloc")
+                self._own = int(base.value)
+            except Exception as ex:                      # noqa: BLE001
+                err = ex
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self._bases = []
+            dist.all_gather_object(handles, bytes(handle.raw) if err is None else None, group=group)
+            if err is None and any(h is None for h in handles):
+                err = RuntimeError("a peer could not allocate its dataset buffer")
             for r, h in enumerate(handles):
-                if r == self.rank:
-                    self._bases.append(self._own)
+                if r == self.rank or err is not None:
+                    self._bases.append(self._own if r == self.rank else 0)
                     continue
-                ptr = C.c_void_p()
-                _cabi.check(lib.ops_peer_open(C.create_string_buffer(h, 64), C.byref(ptr)), f"ops_peer_open(rank {r})")
-                self._bases.append(int(ptr.value))
+                try:
+                    ptr = C.c_void_p()
+                    _cabi.check(lib.ops_peer_open(C.create_string_buffer(h, 64), C.byref(ptr)), f"ops_peer_open(rank {r})")
+                    self._bases.append(int(ptr.value))
+                except Exception as ex:                  # noqa: BLE001
+                    err = ex
+                    self._bases.append(0)
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                for r, b in enumerate(self._bases):
+                    if b and r != self.rank:
+                        lib.ops_peer_close(b)
+                dist.barrier(group=group)
+                if self._own:
+                    lib.ops_peer_free(self._own)
+                self._bases = None
+                raise PeerUnavailable(f"peer-visible dataset buffers are not available on this box: {err}")
         # destination 0 = this GPU's own arrays (the kernel writes the record there and copies the rows to the
         # others); the peers follow in ring order so that the ranks do not all store to the same GPU at once
         self._dests = (_cabi.OpsBeamOptRecordArrays * self.world)()
