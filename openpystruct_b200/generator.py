@@ -73,14 +73,50 @@ def _require_cuda(device) -> torch.device:
     return dev
 
 
-def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device="cuda") -> dict:
-    """Pack sampled cases, copy them to the GPU, run the fused loop, bring the results back (numpy)."""
+def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device="cuda",
+                   distributed: Optional[bool] = None) -> dict:
+    """Pack sampled cases, copy them to the GPU, run the fused loop, bring the results back (numpy).
+
+    Under ``torchrun`` (an initialised process group with more than one rank; ``distributed=False`` opts out)
+    every rank must call this with the SAME cases -- they come from one seeded stream -- and the beams are
+    sharded over the ranks' GPUs: contiguous blocks, no per-iteration communication, the dataset gather fused
+    into the kernel's record write where the GPUs can map each other's memory, the NCCL gather otherwise
+    (``distributed.py``).  Every rank gets the whole dataset back, bit-identical to the single-GPU run."""
     dev = _require_cuda(device)
     fixed, fn, fv, L = sampling.pack_cases(params.num_nodes, params.max_forces, cases, params.num_cases)
     t = lambda a: torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)   # noqa: E731
+    import torch.distributed as dist
+    if distributed is None:
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if distributed:
+        from . import distributed as _dist
+        inputs = {"fixed_uy": t(fixed), "force_nodes": t(fn), "force_vals": t(fv), "L": t(L)}
+        host = None
+        try:
+            ds = _dist.PeerDataset(params, int(L.shape[0]), device=dev)
+        except _dist.PeerUnavailable:                          # raised on every rank alike
+            ds = None
+        if ds is not None:
+            try:
+                start, stop, _per = _dist.shard_bounds(int(L.shape[0]), dist.get_rank(), dist.get_world_size())
+                out = ds.optimise({k: v[start:stop].contiguous() for k, v in inputs.items()}, start)
+                host = {k: v.cpu() for k, v in out.items()}      # (copies: the tensors alias the peer buffer)
+            except _cabi_error() as ex:                        # a configuration whose kernel has no scatter instance
+                if "OPS_E_UNSUPP" not in str(ex):
+                    raise
+            finally:
+                ds.close()
+        if host is None:
+            host = {k: v.cpu() for k, v in _dist.optimise_beams_sharded(params, inputs).items()}
+        return {k: v.numpy() for k, v in host.items()}
     out = _ops.optimise_beams(params, t(fixed), t(fn), t(fv), t(L))
     host = {k: v.cpu() for k, v in out.items()}
     return {k: v.numpy() for k, v in host.items()}
+
+
+def _cabi_error():
+    from ._cabi import CudaLibraryError
+    return CudaLibraryError
 
 
 def make_records(params: BeamOptParams, cases: Sequence[sampling.Case], out: dict) -> List[Optional[dict]]:

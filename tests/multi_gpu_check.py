@@ -46,6 +46,25 @@ def main():
         if rank == 0:
             print(f"multi_gpu_check ok: {script} x{cases_per_beam} {count} beams on {world} GPUs, "
                   f"epochs {int(want['epochs'].min())}..{int(want['epochs'].max())}", flush=True)
+    # the host-level entry under torchrun: every rank draws the same seeded cases, the beams are sharded, every rank
+    # gets the whole dataset -- equal to the single-GPU run of all beams on this rank
+    from openpystruct_b200 import generator
+    from openpystruct_b200.generator import GeneratorConfig
+    cfg = GeneratorConfig.multi_core()
+    a = generator.generate_columnar(cfg, 1500, seed=3, device=dev)
+    rollers, avail = sampling.fixed_bridge(cfg.params.num_nodes, cfg.roller_nodes)
+    import random
+    rng = random.Random(3)
+    cases = [sampling.sample_case(cfg.params.num_nodes, cfg.random_bridge, cfg.L_max, rollers, avail, L_max=cfg.L_max,
+                                  L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max, M_forces_max=cfg.M_forces_max,
+                                  max_force=cfg.max_force, min_force=cfg.min_force, rng=rng) for _ in range(1500)]
+    single = generator.optimise_cases(cfg.params, cases, dev, distributed=False)
+    multi = generator.optimise_cases(cfg.params, cases, dev)
+    for k in single:
+        assert np.array_equal(single[k], multi[k]), (rank, "optimise_cases", k)
+    assert len(a["I_values"]) == int((single["status"] == 0).sum())
+    if rank == 0:
+        print(f"multi_gpu_check ok: generate_columnar / optimise_cases under torchrun == single GPU ({world} GPUs)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
