@@ -892,8 +892,8 @@ struct OpsBeamOptSession {
     OpsBeamOptParams p;
     int64_t max_beams;
     int device;
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
+    cudaStream_t stream, copy;           // launches / device->host copies of finished chunks
+    cudaEvent_t ev0, ev1, evc;
     unsigned char *dbuf, *hbuf;          // one device and one pinned host allocation, same offsets
     size_t in_bytes, out_bytes, ws_bytes;
     size_t o_fixed, o_fn, o_fv, o_L, o_I, o_defl, o_rot, o_sh, o_mo, o_ep, o_loss, o_st, o_sched, o_ws;
@@ -926,8 +926,10 @@ int ops_beamopt_session_create(const OpsBeamOptParams *p, int64_t max_beams, int
     if (s->ws_bytes == 0) { rc = OPS_E_BADARG; goto done; }
     s->o_ws = take(s->ws_bytes);
     OPS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    OPS_CUDA(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
     OPS_CUDA(cudaEventCreate(&s->ev0));
     OPS_CUDA(cudaEventCreate(&s->ev1));
+    OPS_CUDA(cudaEventCreateWithFlags(&s->evc, cudaEventDisableTiming));
     OPS_CUDA(cudaMalloc((void **)&s->dbuf, off));
     OPS_CUDA(cudaHostAlloc((void **)&s->hbuf, host_bytes, cudaHostAllocDefault));
     memset(s->hbuf, 0, host_bytes);
@@ -955,6 +957,33 @@ int ops_beamopt_session_arrays(OpsBeamOptSession *s, OpsBeamOptHostArrays *a)
     return 0;
 }
 
+// Beams per launch of a session run.  A run is a pipeline: the whole batch's inputs go up, then the batch is optimised
+// in chunks of whole rounds (a round = the beams resident on the GPU at once) and every chunk's record comes down on a
+// second stream while the next chunk iterates, so only the last chunk's device->host copy is exposed.  With fixed
+// epochs a chunk is one round (three of the 384-thread instance); with early stopping it is at least six, because a
+// launch ends with its slowest beam and refills its groups only from its own chunk.  B itself = no pipelining.
+static int64_t session_chunk_beams(const OpsBeamOptSession *s, int64_t B)
+{
+    BeamConsts k;
+    if (make_consts(&s->p, &k) != 0) return B;
+    LaunchPlan pl;
+    if (plan_launch(k, s->p.num_cases, B, s->p.solver, &pl) != 0) return B;
+    int64_t per_round = 0;
+    int rounds = 1;
+    if (pl.lanes) {
+        per_round = (int64_t)pl.lp.blocks * (pl.lp.threads / (lanes::LPB * s->p.num_cases));
+        if (pl.lp.threads > 320) rounds = 3;
+    } else if (pl.wide) {
+        per_round = (int64_t)pl.wp.blocks * (pl.wp.threads / pl.wp.lpb);
+    } else {
+        return B;
+    }
+    if (s->p.early_stop && rounds < 6) rounds = 6;
+    const int64_t chunk = per_round * rounds;
+    if (chunk <= 0 || B < chunk + chunk / 4) return B;
+    return chunk;
+}
+
 int ops_beamopt_session_run(OpsBeamOptSession *s, int64_t B, float *elapsed_ms)
 {
     if (!s || B < 0 || B > s->max_beams) return OPS_E_BADARG;
@@ -964,7 +993,11 @@ int ops_beamopt_session_run(OpsBeamOptSession *s, int64_t B, float *elapsed_ms)
     const size_t F = (size_t)s->p.max_forces * C, b = (size_t)B;
     unsigned char *d = s->dbuf, *h = s->hbuf;
     auto h2d = [&](size_t o, size_t bytes) { return cudaMemcpyAsync(d + o, h + o, bytes, cudaMemcpyHostToDevice, s->stream); };
-    auto d2h = [&](size_t o, size_t bytes) { return cudaMemcpyAsync(h + o, d + o, bytes, cudaMemcpyDeviceToHost, s->stream); };
+    auto d2h = [&](size_t o, size_t first, size_t rows, size_t row_bytes) {       // rows [first, first + rows) of an output
+        return cudaMemcpyAsync(h + o + first * row_bytes, d + o + first * row_bytes, rows * row_bytes,
+                               cudaMemcpyDeviceToHost, s->copy);
+    };
+    const int64_t chunk = session_chunk_beams(s, B);
     OPS_CUDA(cudaSetDevice(s->device));
     if (B == s->max_beams) {
         OPS_CUDA(h2d(0, s->in_bytes));
@@ -974,24 +1007,30 @@ int ops_beamopt_session_run(OpsBeamOptSession *s, int64_t B, float *elapsed_ms)
         OPS_CUDA(h2d(s->o_L, b * 8));
     }
     OPS_CUDA(cudaEventRecord(s->ev0, s->stream));
-    rc = ops_beamopt_launch(&s->p, B, d + s->o_fixed, (const int32_t *)(d + s->o_fn), (const double *)(d + s->o_fv),
-                            (const double *)(d + s->o_L), (const float *)(d + s->o_sched), (float *)(d + s->o_I),
-                            (double *)(d + s->o_defl), (double *)(d + s->o_rot), (float *)(d + s->o_sh),
-                            (float *)(d + s->o_mo), (int32_t *)(d + s->o_ep), (float *)(d + s->o_loss),
-                            (int32_t *)(d + s->o_st), d + s->o_ws, s->ws_bytes, s->stream);
-    if (rc) goto done;
-    OPS_CUDA(cudaEventRecord(s->ev1, s->stream));
-    if (B == s->max_beams) {
-        OPS_CUDA(d2h(s->in_bytes, s->out_bytes));
-    } else {
-        OPS_CUDA(d2h(s->o_I, b * n * 4)); OPS_CUDA(d2h(s->o_defl, b * C * nn * 8)); OPS_CUDA(d2h(s->o_rot, b * C * nn * 8));
-        OPS_CUDA(d2h(s->o_sh, b * C * n * 4)); OPS_CUDA(d2h(s->o_mo, b * C * n * 4));
-        OPS_CUDA(d2h(s->o_ep, b * 4)); OPS_CUDA(d2h(s->o_loss, b * 4)); OPS_CUDA(d2h(s->o_st, b * 4));
+    for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+        const size_t f = (size_t)r0, m = (size_t)((B - r0) < chunk ? (B - r0) : chunk);
+        rc = ops_beamopt_launch(&s->p, (int64_t)m, d + s->o_fixed + f * nn, (const int32_t *)(d + s->o_fn) + f * F,
+                                (const double *)(d + s->o_fv) + f * F, (const double *)(d + s->o_L) + f,
+                                (const float *)(d + s->o_sched), (float *)(d + s->o_I) + f * n,
+                                (double *)(d + s->o_defl) + f * C * nn, (double *)(d + s->o_rot) + f * C * nn,
+                                (float *)(d + s->o_sh) + f * C * n, (float *)(d + s->o_mo) + f * C * n,
+                                (int32_t *)(d + s->o_ep) + f, (float *)(d + s->o_loss) + f, (int32_t *)(d + s->o_st) + f,
+                                d + s->o_ws, s->ws_bytes, s->stream);
+        if (rc) goto done;
+        // this chunk's record goes down on the copy stream as soon as its launch has finished
+        OPS_CUDA(cudaEventRecord(s->evc, s->stream));
+        OPS_CUDA(cudaStreamWaitEvent(s->copy, s->evc, 0));
+        OPS_CUDA(d2h(s->o_I, f, m, n * 4)); OPS_CUDA(d2h(s->o_defl, f, m, C * nn * 8)); OPS_CUDA(d2h(s->o_rot, f, m, C * nn * 8));
+        OPS_CUDA(d2h(s->o_sh, f, m, C * n * 4)); OPS_CUDA(d2h(s->o_mo, f, m, C * n * 4));
+        OPS_CUDA(d2h(s->o_ep, f, m, 4)); OPS_CUDA(d2h(s->o_loss, f, m, 4)); OPS_CUDA(d2h(s->o_st, f, m, 4));
     }
+    OPS_CUDA(cudaEventRecord(s->ev1, s->stream));
     OPS_CUDA(cudaStreamSynchronize(s->stream));
+    OPS_CUDA(cudaStreamSynchronize(s->copy));
     if (elapsed_ms) OPS_CUDA(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
 done:
     if (rc > 0) cudaGetLastError();
+    if (rc) { cudaStreamSynchronize(s->stream); cudaStreamSynchronize(s->copy); }
     return rc;
 }
 
@@ -1004,6 +1043,8 @@ void ops_beamopt_session_destroy(OpsBeamOptSession *s)
     if (s->hbuf) cudaFreeHost(s->hbuf);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->evc) cudaEventDestroy(s->evc);
+    if (s->copy) { cudaStreamSynchronize(s->copy); cudaStreamDestroy(s->copy); }
     if (s->stream) cudaStreamDestroy(s->stream);
     free(s);
 }

@@ -333,6 +333,26 @@ def test_session_matches_the_device_pointer_entry():
         assert s.kernel_ms > 0
 
 
+@pytest.mark.parametrize("early_stop", [False, True])
+def test_session_pipeline_of_chunked_launches(early_stop):
+    """A session run is a pipeline: launches of whole rounds with each chunk's device->host copy on a second
+    stream under the next chunk's iterations.  Whatever the chunking (fixed epochs: one round per launch, early
+    stopping: six), the pinned outputs hold the bytes of the single device-pointer launch."""
+    p = BeamOptParams.for_script("MC").replace(max_e=40 if not early_stop else 600, early_stop=early_stop)
+    B = 148 * 40 * 2 + 1776 if not early_stop else 148 * 48 * 6 * 2 + 999        # three launches either way
+    cases = seeded_cases(p, 4096, seed=108)
+    f0, n0, v0, L0 = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    rep = (B + 4095) // 4096
+    fixed, fn, fv, L = (np.concatenate([a] * rep)[:B] for a in (f0, n0, v0, L0))
+    want = gpu_run(p, fixed, fn, fv, L)
+    with _cabi.Session(p, B, device=0) as s:
+        for Bi in (B, B - 333):
+            s.load(fixed[:Bi], fn[:Bi], fv[:Bi], L[:Bi])
+            got = s.run(Bi)
+            for k in want:
+                assert np.array_equal(got[k], want[k][:Bi]), (k, Bi)
+
+
 @pytest.mark.parametrize("num_cases", [2, 4, 8])
 def test_shared_inertia_load_cases(num_cases):
     """BASELINE config 4 (extension): C load cases per beam share one I vector, summed
