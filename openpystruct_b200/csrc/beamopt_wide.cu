@@ -253,7 +253,7 @@ beamopt_wide_kernel(const BeamConsts k, const long long B, const OptPtrs p, cons
 // host side
 // ---------------------------------------------------------------------------------------------
 #ifndef OPS_WIDE32_MAXT
-#define OPS_WIDE32_MAXT 512
+#define OPS_WIDE32_MAXT 384     // 168-register cap (3 warps per SM sub-partition): +7 % on 1000-element beams over 512 / 128
 #endif
 constexpr int WIDE8_MAXT = 512, WIDE32_MAXT = OPS_WIDE32_MAXT;
 
