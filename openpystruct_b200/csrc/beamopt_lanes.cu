@@ -68,8 +68,9 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
         have = false;                                                                                                \
     }
 // SC: instance with the in-kernel dataset gather (the peers' copies of a finished beam's rows).  A separate
-// instance because the mere presence of that cold code costs the 320-thread instance 4.7 % on 10 000 beams (same
-// epoch-loop instructions, different code placement; profiles/r01_v6_ab_scatter.txt).
+// instance because the mere presence of that cold code -- wherever it is placed -- costs the 320-thread instance
+// 4-7 % on 10 000 beams: same epoch-loop instruction count, but ptxas orders the loop differently and ncu shows
+// 10 % more fixed-latency `wait` stalls (profiles/r01_v6_ab_scatter.txt, r01_v6_scatter_instance_ncu.md).
 // TFIX: compile-time CTA size (0 = blockDim.x).  With it every shared-memory column stride is an immediate
 // and the [slot][thread] addressing costs no integer instructions.
 template <int EPL, int NFIX, int NC, int TFIX, bool SC>
@@ -213,10 +214,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
         // 48 KB range -- best for many-round batches (384-thread instance, +2.6 % on 1 M beams) and no worse for the
         // scatter instances; the 320-thread instance that runs 10 000 beams in 1.7 rounds is 4 % faster with the
         // record path between the loss and the Adam step.
-#ifndef OPS_ADAM_FIRST_SC
-#define OPS_ADAM_FIRST_SC 1
-#endif
-        constexpr bool ADAM_FIRST = (SC && OPS_ADAM_FIRST_SC) || TFIX == LANES_BIG_THREADS;
+        constexpr bool ADAM_FIRST = SC || TFIX == LANES_BIG_THREADS;
         if (ADAM_FIRST) {
             if (have && !done) lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
             if (have && done) {
@@ -313,7 +311,7 @@ static cudaError_t launch_single_case(const BeamConsts &k, long long B, const Op
 
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream)
 {
-    const bool sc = p.dest.nd > 1;
+    const bool sc = p.dest.nd > 1 || getenv("OPS_FORCE_SC") != nullptr;      // (the knob: profiling of the scatter instances on one GPU)
     if (sc && !lanes_scatter_supported(pl)) return cudaErrorInvalidValue;
     if (pl.num_cases > 1) {
         // load cases sharing one inertia vector: the 100-element discretisation and the generic <= 104-element one
