@@ -58,7 +58,7 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
                 p.status[row] = bad;                                                                                 \
             }                                                                                                        \
         }                                                                                                            \
-        if (t > 0) lane_adam<EPL, false>(k, rg, ls, pc, neg_step, bc2_sqrt);                                         \
+        if (t > 0) lane_adam<EPL, false, NBK>(k, rg, ls, pc, neg_step, bc2_sqrt);                                         \
         if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + row * n);                                   \
         if (SC && p.dest.nd > 1) { /* dataset gather: every lane re-reads rows other lanes wrote */                  \
             __syncwarp(gmask);                                                                                       \
@@ -78,6 +78,10 @@ __global__ void __launch_bounds__(TFIX ? TFIX : LANES_MAX_THREADS, 1)
 beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // Slots per stage-major batch.  Five everywhere except the 320-thread scatter instance, whose epoch loop ptxas orders
+    // best with six (4.86-5.06 ms against 5.39-5.41 ms with five on 10 000 beams; the plain instances are 4-6 % slower
+    // with six): same arithmetic, same bits -- only the instruction order differs (profiles/r01_v6_ab_scatter.txt).
+    constexpr int NBK = (SC && TFIX == LANES_MAX_THREADS) ? 6 : lanes::NB;
     const int T = TFIX ? TFIX : (int)blockDim.x, G = T / LPB;
     const int tid = threadIdx.x, l = tid & (LPB - 1), g = tid / LPB;
     const unsigned gmask = 0xffu << (tid & 24);
@@ -195,7 +199,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             if (NC * LPB <= 32) __syncwarp();
             else if (run) team_sync<NC>(team_mask, barrier_id);    // whole warps belong to one team: uniform
         }
-        if (run) lane_forces<EPL, NC>(k, n, rg, ls, gs, fb.invLe, l, case_id);
+        if (run) lane_forces<EPL, NC, NBK>(k, n, rg, ls, gs, fb.invLe, l, case_id);
         if (NC * LPB <= 32) __syncwarp();                           // (NC > 1: exchange columns are rewritten next epoch)
         else if (run) team_sync<NC>(team_mask, barrier_id);
         if (run) {
@@ -216,13 +220,13 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
         // record path between the loss and the Adam step.
         constexpr bool ADAM_FIRST = SC || TFIX == LANES_BIG_THREADS;
         if (ADAM_FIRST) {
-            if (have && !done) lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
+            if (have && !done) lane_adam<EPL, true, NBK>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
             if (have && done) {
                 OPS_RECORD_PATH
             }
         } else if (have) {
             if (!done) {
-                lane_adam<EPL, true>(k, rg, ls, pc, neg_step, bc2_sqrt);
+                lane_adam<EPL, true, NBK>(k, rg, ls, pc, neg_step, bc2_sqrt);
             } else {
                 OPS_RECORD_PATH
             }

@@ -406,10 +406,11 @@ OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, cons
 // NC > 1: the squares come from the exchange columns of the team (case_id = this group's case).
 // fp32 ranges for the branch-free division / square root: I in [clamp_min, 1e20) (the clamp,
 // SingleCore:208), c = M^2 and h = V^2 zero or >= 2^-100.
-template <int EPL, int NC>
+template <int EPL, int NC, int NBX = NB>
 OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe,
                         int l, int case_id)
 {
+    constexpr int NB = NBX;                     // slots per batch of this instance (shadows the default)
     const SumShape sh = sum_shape(n);
     float aI[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ad[4] = {0.0f, 0.0f, 0.0f, 0.0f}, aq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float tI = 0.0f, td = 0.0f, tq = 0.0f;
@@ -527,10 +528,11 @@ OPS_HD float group_loss(const BeamConsts &k, int n, const LaneStore &ls, int l)
 // The fast square root needs v >= 2^-101; v is an EMA of g^2, so anything smaller means g vanished on
 // every epoch so far -- tested once per lane and epoch, with the generic operators as the (cold)
 // alternative.
-template <int EPL, bool PASS1>
+template <int EPL, bool PASS1, int NBX = NB>
 OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc,
                       float neg_step, float bc2_sqrt)
 {
+    constexpr int NB = NBX;
     bool rare = false;
     {
         float t0[EPL], t1[EPL];
