@@ -211,3 +211,33 @@ def test_peer_copy_of_a_record_moves_exactly_its_rows(num_nodes, num_cases):
             want[k][row] = src[k][row]
     for k in order:
         assert np.array_equal(want[k], dst[k]), k
+
+
+def test_batch_size_of_the_stage_major_batches_does_not_change_the_bits(tmp_path):
+    """The kernel instances differ in the number of slots per stage-major batch (five; six in the 320-thread
+    scatter instance): a pure reordering of independent per-element chains.  The same source built with six and with
+    four slots per batch produces the bits of the default build (single case and four load cases)."""
+    import ctypes as C
+    import subprocess
+    from tests import helpers
+    base = helpers.hostsim_lib()
+    libs = {}
+    for nb in (4, 6):
+        path = str(tmp_path / f"libhostsim_nb{nb}.so")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                        f"-DOPS_LANES_NB={nb}", "-o", path, helpers._HS_SRC], check=True)
+        libs[nb] = C.CDLL(path)
+    for num_cases, beams in ((1, 24), (4, 8)):
+        p = BeamOptParams.for_script("MC").replace(num_cases=num_cases, max_e=150)
+        cases = helpers.seeded_cases(p, beams * num_cases, seed=41)
+        fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases, num_cases)
+        want = hostsim_run(p, fixed, fn, fv, L, solver=0)
+        for nb, lib in libs.items():
+            helpers._hs, keep = lib, helpers._hs
+            try:
+                got = hostsim_run(p, fixed, fn, fv, L, solver=0)
+            finally:
+                helpers._hs = keep
+            for k in want:
+                assert np.array_equal(want[k], got[k]), (nb, num_cases, k)
+    assert helpers._hs is base
