@@ -247,7 +247,14 @@ class PeerDataset:
             dist.all_reduce(self._flag, group=self.group)      # every rank's kernel, hence every record, has landed
         return self.tensors()
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def close(self):
+        """Collective: unmap the peers' buffers, then free this rank's (every rank must call it)."""
         if getattr(self, "_bases", None) is None:
             return
         lib = self._cabi.lib()

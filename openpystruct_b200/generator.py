@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import ops as _ops
+from ._cabi import CudaLibraryError
 from . import sampling
 from .params import BeamOptParams
 
@@ -101,7 +102,7 @@ def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device
                 start, stop, _per = _dist.shard_bounds(int(L.shape[0]), dist.get_rank(), dist.get_world_size())
                 out = ds.optimise({k: v[start:stop].contiguous() for k, v in inputs.items()}, start)
                 host = {k: v.cpu() for k, v in out.items()}      # (copies: the tensors alias the peer buffer)
-            except _cabi_error() as ex:                        # a configuration whose kernel has no scatter instance
+            except CudaLibraryError as ex:                     # a configuration whose kernel has no scatter instance
                 if "OPS_E_UNSUPP" not in str(ex):
                     raise
             finally:
@@ -112,11 +113,6 @@ def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device
     out = _ops.optimise_beams(params, t(fixed), t(fn), t(fv), t(L))
     host = {k: v.cpu() for k, v in out.items()}
     return {k: v.numpy() for k, v in host.items()}
-
-
-def _cabi_error():
-    from ._cabi import CudaLibraryError
-    return CudaLibraryError
 
 
 def make_records(params: BeamOptParams, cases: Sequence[sampling.Case], out: dict) -> List[Optional[dict]]:
