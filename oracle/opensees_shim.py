@@ -15,6 +15,9 @@ not installable in this image, so its published algorithm is restated here:
 * ``LoadControl 1.0`` + ``Linear`` algorithm: one linear solve at load factor 1.0,
 * ``eleResponse(e, 'forces')``: global resisting force of the element, fixed-end terms included.
 
+* ``BandGeneral`` (LAPACK ``dgbsv`` through ``scipy.linalg.solve_banded``) for the frame optimiser
+  (OpenPyStruct_FrameOpt_Discrete_Beta.py:75-139; elements of any orientation, grounded nodes ``fix(tag,1,1,1)``).
+
 Call sites restated (reference file:line):
   SingleCore:93-124 (setup_model), :176-190 (wipe/analysis/analyze/eleResponse), :224-232 (nodeDisp)
   MultiCore:97-128, :177-191, :222-223 ; GPU:98-129, :138, :185-207, :246-250 ; BeamOpt:95-126, :136-142
@@ -28,7 +31,7 @@ The module keeps OpenSees' process-global domain semantics (one model, ``wipe()`
 from __future__ import annotations
 
 import numpy as np
-from scipy.linalg import solveh_banded
+from scipy.linalg import solve_banded, solveh_banded
 
 __all__ = [
     "wipe", "model", "node", "fix", "geomTransf", "element", "timeSeries", "pattern",
@@ -267,13 +270,25 @@ def analyze(nsteps=1):
         Kff = K[np.ix_(fidx, fidx)]
         ff = f[fidx]
         n = len(fidx)
-        # BandSPD: upper banded storage for dpbsv.
         kd = min(hbw, n - 1)
-        ab = np.zeros((kd + 1, n))
-        for d in range(kd + 1):
-            ab[kd - d, d:] = np.diagonal(Kff, d)
         try:
-            uf = solveh_banded(ab, ff, lower=False, check_finite=True)
+            if _D.system == "BandGeneral":
+                # BandGeneral: LAPACK dgbsv (band LU with partial pivoting), the frame optimiser's system
+                # (OpenPyStruct_FrameOpt_Discrete_Beta.py:132)
+                gb = np.zeros((2 * kd + 1, n))
+                for d in range(-kd, kd + 1):
+                    diag = np.diagonal(Kff, d)
+                    if d >= 0:
+                        gb[kd - d, d:] = diag
+                    else:
+                        gb[kd - d, :n + d] = diag
+                uf = solve_banded((kd, kd), gb, ff, check_finite=True)
+            else:
+                # BandSPD: upper banded storage for dpbsv.
+                ab = np.zeros((kd + 1, n))
+                for d in range(kd + 1):
+                    ab[kd - d, d:] = np.diagonal(Kff, d)
+                uf = solveh_banded(ab, ff, lower=False, check_finite=True)
         except Exception:
             return -3
         u = np.zeros(ndof)

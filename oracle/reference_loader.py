@@ -105,3 +105,77 @@ def run_reference_sample(which: str, seed: int, *, flag: int = 0, patience=None,
                                  "alpha_shear", "tolerance", "patience", "L_min", "N_rollers_max",
                                  "M_forces_max")}
     return result, tr, params
+
+
+# ------------------------------------------------------------------------------------------------
+# Frame optimiser (groundwork for the next round): OpenPyStruct_FrameOpt_Discrete_Beta.py
+# is one flat script -- geometry drawn with ``random.randint`` (:50-51), Adam loop at module level (:179-206),
+# then matplotlib plots.  It is executed verbatim up to the plots on top of the shim.
+# ------------------------------------------------------------------------------------------------
+FRAME_SCRIPT = "OpenPyStruct_FrameOpt_Discrete_Beta.py"
+
+
+class _Anything:
+    """Stand-in for matplotlib.pyplot (absent in this image): every attribute is a no-op callable."""
+
+    def __getattr__(self, name):
+        return self
+
+    def __call__(self, *a, **k):
+        return self
+
+
+def frame_reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_DIR, FRAME_SCRIPT))
+
+
+def run_reference_frame(seed: int, overrides=None):
+    """random.seed(seed); the reference frame script up to its plots.  ``overrides``: text-level replacements of
+    module constants, e.g. {"num_epochs  = 5000": "num_epochs  = 300"} (the script has no functions to call).
+    Returns (namespace, Trace): the namespace holds num_bays, num_stories, loss_history, opt_I, best_loss, ..."""
+    import io
+    import contextlib
+    _install_shim()
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = _Anything()
+    mpl.__path__ = []
+    saved = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.pyplot")}
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pyplot"] = mpl.pyplot
+    path = os.path.join(REFERENCE_DIR, FRAME_SCRIPT)
+    with open(path, "r") as fh:
+        text = fh.read()
+    cut = text.index("# Plot Loss History")
+    cut = text.rindex("##############################", 0, cut)
+    text = text[:cut]
+    for old, new in (overrides or {}).items():
+        if old not in text:
+            raise KeyError(old)
+        text = text.replace(old, new)
+    tr = Trace()
+    real_analyze = opensees_shim.analyze
+
+    def analyze(n=1):
+        rc = real_analyze(n)
+        if rc == 0:
+            d = opensees_shim._D
+            tags = sorted(d.elements)
+            tr.I.append([d.elements[t][4] for t in tags])
+            tr.M.append([float(d.ele_forces[t][2]) for t in tags])
+            tr.V.append([float(d.ele_forces[t][1]) for t in tags])
+        return rc
+
+    opensees_shim.analyze = analyze
+    ns = {"__name__": "_reference_frame", "__file__": path}
+    try:
+        random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            exec(compile(text, path, "exec"), ns)
+    finally:
+        opensees_shim.analyze = real_analyze
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return ns, tr
