@@ -96,3 +96,40 @@ def test_port_reproduces_the_reference_runs(key):
     assert r["epochs"] == epochs
     assert np.array_equal(r["loss"], g[key + "_loss"])
     assert np.array_equal(r["I"], g[key + "_I"])
+
+
+@pytest.mark.parametrize("bays,stories", [(1, 1), (1, 2), (4, 5), (8, 9), (10, 10)])
+def test_band_restatement_of_the_frame_solve_matches_the_shim(bays, stories):
+    """oracle/frame_fe.py (DOFs at the elevated nodes only, closed-form global element matrices, band Cholesky) against
+    the shim's dense assembly + BandGeneral on random inertias: displacements and the end forces the loss reads."""
+    from oracle import frame_fe
+    p = fp.FrameParams()
+    nodes, elements, n_col = fp.frame_topology(bays, stories, p)
+    rng = np.random.default_rng(bays * 100 + stories)
+    I = np.exp(rng.uniform(np.log(1e-5), np.log(0.5), len(elements)))
+    assert fp.build_and_solve(nodes, elements, n_col, list(I), p) == 0
+    u, forces = frame_fe.frame_solve(bays, stories, I, p)
+    want_u = np.array([ops.nodeDisp(t) for t in sorted(nodes) if nodes[t][1] != 0.0])
+    want_f = np.array([ops.eleResponse(t, 'forces') for t, _, _ in elements])
+    assert np.max(np.abs(u - want_u)) <= 1e-9 * np.max(np.abs(want_u))
+    scale = np.max(np.abs(want_f))
+    assert np.max(np.abs(forces - want_f)) <= 1e-8 * scale
+
+
+def test_partial_gradient_closed_form_is_what_autograd_computes():
+    import torch
+    from oracle import frame_fe
+    p = fp.FrameParams()
+    rng = np.random.default_rng(3)
+    n = 40
+    I = np.exp(rng.uniform(np.log(1e-5), np.log(0.5), n)); M = rng.normal(0, 5e4, n); V = rng.normal(0, 3e4, n)
+    It = torch.tensor(I, dtype=torch.float64, requires_grad=True)
+    e_m, e_v = 0.0, 0.0
+    for e in range(n):
+        e_m = e_m + (M[e] ** 2) / (2 * p.E * It[e] + 1e-8)
+        e_v = e_v + (V[e] ** 2) / (p.G * (p.k * (It[e] ** 0.5)))
+    total = torch.sum(It) + p.alpha_moment * e_m + p.alpha_shear * e_v
+    total.backward()
+    want_total, want_grad = frame_fe.frame_loss_and_partial_gradient(I, M, V, p)
+    assert float(total.detach()) == pytest.approx(want_total, rel=1e-13)
+    assert np.allclose(It.grad.numpy(), want_grad, rtol=1e-12, atol=0)
