@@ -279,6 +279,21 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+    gather_check = None
+    if peer is not None:
+        # Driver-visible identity of the in-kernel dataset gather (one warm-up step, outside the timed region): the
+        # dataset the kernels scattered into THIS rank's arrays over NVLink must equal, byte for byte, the NCCL
+        # all_gather of the per-rank results -- on every rank, or the run fails loudly.
+        got = {k_: v_.clone() for k_, v_ in step().items()}
+        want = gather_outputs(ops.optimise_beams(p, *d_in), B * world)
+        bad = [k_ for k_ in want if not torch.equal(got[k_].view(torch.uint8), want[k_].view(torch.uint8))]
+        flag_t = torch.tensor([len(bad)], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag_t, op=dist.ReduceOp.MAX)
+        if int(flag_t.item()) != 0:
+            raise SystemExit(f"bench.py: rank {rank}: the in-kernel dataset gather differs from the NCCL gather in {bad}")
+        gather_check = {"in_kernel_gather_equals_nccl_all_gather": True, "ranks": world, "rows": int(B * world),
+                        "bytes_compared_per_rank": int(sum(v_.numel() * v_.element_size() for v_ in want.values()))}
+        del got, want
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -413,6 +428,7 @@ def run_ours(args):
                        "two 4-byte all_reduce barriers per step" if peer is not None else
                        "NCCL all_gather of the dataset after the kernel, every step")},
         "clocks": clocks,
+        "gather_check": gather_check,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "path": "ops_beamopt_session_run (C ABI; pinned host buffers, H2D of the inputs + launch + D2H of the "
                         "whole record inside every step)",

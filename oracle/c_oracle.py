@@ -113,13 +113,17 @@ def beamopt(p: Params, fixed_uy, force_nodes, force_vals, L, fe_precision: int =
         "I": np.zeros((B, n), np.float32), "defl": np.zeros((B, Cc, nn)), "rot": np.zeros((B, Cc, nn)),
         "shear": np.zeros((B, Cc, n), np.float32), "moment": np.zeros((B, Cc, n), np.float32),
         "epochs": np.zeros(B, np.int32), "loss": np.zeros(B, np.float32), "status": np.zeros(B, np.int32),
+        # smallest early-stop decision margin of the run in fp32 ulps of the loss (oracle-side diagnostic, no product
+        # counterpart): a stop epoch may legitimately differ only where this is about one ulp
+        "margin_ulps": np.full(B, np.inf),
     }
-    rc = lib().oracle_beamopt_prec(C.byref(p), C.c_int64(B), _p(fixed_uy, C.c_uint8), _p(force_nodes, C.c_int32),
-                              _p(force_vals, C.c_double), _p(L, C.c_double), _p(out["I"], C.c_float),
-                              _p(out["defl"], C.c_double), _p(out["rot"], C.c_double),
-                              _p(out["shear"], C.c_float), _p(out["moment"], C.c_float),
-                              _p(out["epochs"], C.c_int32), _p(out["loss"], C.c_float),
-                              _p(out["status"], C.c_int32), C.c_int(fe_precision))
+    rc = lib().oracle_beamopt_margin(C.byref(p), C.c_int64(B), _p(fixed_uy, C.c_uint8), _p(force_nodes, C.c_int32),
+                                     _p(force_vals, C.c_double), _p(L, C.c_double), _p(out["I"], C.c_float),
+                                     _p(out["defl"], C.c_double), _p(out["rot"], C.c_double),
+                                     _p(out["shear"], C.c_float), _p(out["moment"], C.c_float),
+                                     _p(out["epochs"], C.c_int32), _p(out["loss"], C.c_float),
+                                     _p(out["status"], C.c_int32), C.c_int(fe_precision),
+                                     _p(out["margin_ulps"], C.c_double))
     if rc != 0:
         raise RuntimeError(f"oracle_beamopt rc={rc}")
     return out

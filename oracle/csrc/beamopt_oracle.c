@@ -195,6 +195,10 @@ int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *
                         const int32_t *force_nodes, const double *force_vals, const double *L,
                         float *I_out, double *defl, double *rot, float *shear, float *moment,
                         int32_t *epochs, float *loss, int32_t *status, int fe_precision);
+int oracle_beamopt_margin(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
+                          const int32_t *force_nodes, const double *force_vals, const double *L,
+                          float *I_out, double *defl, double *rot, float *shear, float *moment,
+                          int32_t *epochs, float *loss, int32_t *status, int fe_precision, double *min_margin_ulps);
 
 int oracle_beamopt(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
                    const int32_t *force_nodes, const double *force_vals, const double *L,
@@ -210,6 +214,18 @@ int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *
                         float *I_out, double *defl, double *rot, float *shear, float *moment,
                         int32_t *epochs, float *loss, int32_t *status, int fe_precision)
 {
+    return oracle_beamopt_margin(p, B, fixed_uy, force_nodes, force_vals, L, I_out, defl, rot, shear, moment,
+                                 epochs, loss, status, fe_precision, (double *)0);
+}
+
+/* min_margin_ulps (optional): per beam, the smallest |loss_t - (best - tolerance)| over the run's early-stop tests
+ * (SingleCore:211), in units of the fp32 spacing of loss_t -- how many ulps of the loss the closest stop / "new best"
+ * decision of the run was away from going the other way (INFINITY when no test had a finite best). */
+int oracle_beamopt_margin(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
+                          const int32_t *force_nodes, const double *force_vals, const double *L,
+                          float *I_out, double *defl, double *rot, float *shear, float *moment,
+                          int32_t *epochs, float *loss, int32_t *status, int fe_precision, double *min_margin_ulps)
+{
     const int nn = p->num_nodes, n = nn - 1, C = p->num_cases, F = p->max_forces;
     if (nn < 2 || C < 1 || F < 0) return -1;
     float *table = malloc(sizeof(float) * 2 * (size_t)(p->max_epochs > 0 ? p->max_epochs : 1));
@@ -224,7 +240,7 @@ int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *
     for (int64_t b = 0; b < B; ++b) {
         const uint8_t *fx = fixed_uy + b * nn;
         for (int e = 0; e < n; ++e) { I[e] = (float)p->I0; m[e] = 0.0f; v[e] = 0.0f; }
-        double best = INFINITY;
+        double best = INFINITY, margin = INFINITY;
         int counter = 0, ep = 0, st = 0;
         float lossf = NAN;
         for (int t = 0; t < p->max_epochs; ++t) {
@@ -255,10 +271,16 @@ int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *
             ++ep;
             if (p->early_stop) {
                 const double l = (double)lossf;
+                if (isfinite(best) && isfinite(l)) {
+                    const double ulp = (double)nextafterf(fabsf(lossf), INFINITY) - (double)fabsf(lossf);
+                    const double mg = fabs(l - (best - p->tolerance)) / ulp;
+                    if (mg < margin) margin = mg;
+                }
                 if (l < best - p->tolerance) { best = l; counter = 0; } else { ++counter; }
                 if (counter >= p->patience) break;
             }
         }
+        if (min_margin_ulps) min_margin_ulps[b] = margin;
         if (p->zero_last_node)
             for (int c = 0; c < C; ++c) { defl[(b * C + c) * nn + nn - 1] = 0.0; rot[(b * C + c) * nn + nn - 1] = 0.0; }
         memcpy(I_out + b * n, I, sizeof(float) * (size_t)n);

@@ -38,6 +38,11 @@ int oracle_beamopt_prec(const OracleBeamOptParams *p, int64_t B, const uint8_t *
                         const int32_t *force_nodes, const double *force_vals, const double *L,
                         float *I_out, double *defl, double *rot, float *shear, float *moment,
                         int32_t *epochs, float *loss, int32_t *status, int fe_precision);
+/* oracle_beamopt_prec + per beam the smallest early-stop decision margin of the run, in fp32 ulps of the loss */
+int oracle_beamopt_margin(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
+                          const int32_t *force_nodes, const double *force_vals, const double *L,
+                          float *I_out, double *defl, double *rot, float *shear, float *moment,
+                          int32_t *epochs, float *loss, int32_t *status, int fe_precision, double *min_margin_ulps);
 int oracle_beam_solve(const OracleBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
                       const int32_t *force_nodes, const double *force_vals, const double *L,
                       const double *I, double *defl, double *rot, double *shear, double *moment,

@@ -60,6 +60,32 @@ class Trace:
         self.I = []       # element inertias handed to ops.element (fp32 values widened), per epoch
         self.M = []       # eleResponse[2] per element (f64), per epoch
         self.V = []       # eleResponse[1] per element (f64), per epoch
+        self.loss = []    # float(total_loss) per epoch: the fp32 value the early-stop test compares (SingleCore:211)
+
+
+class record_losses:
+    """Context manager: every ``Tensor.backward()`` of a scalar appends ``float(tensor)`` to ``sink`` -- the reference
+    calls ``total_loss.backward()`` exactly once per epoch (SingleCore:202, BeamOpt:169, FrameOpt:196), so this
+    captures the loss trajectory without touching its source."""
+
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __enter__(self):
+        import torch
+        self._torch, self._real = torch, torch.Tensor.backward
+        sink, real = self.sink, self._real
+
+        def backward(t, *a, **k):
+            if t.numel() == 1:
+                sink.append(float(t.detach()))
+            return real(t, *a, **k)
+
+        torch.Tensor.backward = backward
+        return self
+
+    def __exit__(self, *exc):
+        self._torch.Tensor.backward = self._real
 
 
 def run_reference_sample(which: str, seed: int, *, flag: int = 0, patience=None, overrides=None,
@@ -97,7 +123,8 @@ def run_reference_sample(which: str, seed: int, *, flag: int = 0, patience=None,
             kwargs = {"patience": ns["patience"] if patience is None else patience}   # SingleCore:257
         else:
             kwargs = {"patience": ns["patience"] if patience is None else patience, "device": "cpu"}
-        result = ns["generate_sample"](*args, **kwargs)
+        with record_losses(tr.loss):
+            result = ns["generate_sample"](*args, **kwargs)
     finally:
         opensees_shim.analyze = real_analyze
     params = {k: ns[k] for k in ("E", "nu", "G", "A", "L_max", "num_nodes", "max_force", "min_force",
@@ -169,7 +196,7 @@ def run_reference_frame(seed: int, overrides=None):
     ns = {"__name__": "_reference_frame", "__file__": path}
     try:
         random.seed(seed)
-        with contextlib.redirect_stdout(io.StringIO()):
+        with contextlib.redirect_stdout(io.StringIO()), record_losses(tr.loss):
             exec(compile(text, path, "exec"), ns)
     finally:
         opensees_shim.analyze = real_analyze

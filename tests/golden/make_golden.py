@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import opensees_shim                      # noqa: E402
-from oracle.reference_loader import (REFERENCE_DIR, run_reference_sample, _install_shim)  # noqa: E402
+from oracle.reference_loader import (REFERENCE_DIR, run_reference_sample, _install_shim, record_losses)  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -50,7 +50,11 @@ def _record(tag, seed, result, tr, meta):
         "M64_first": np.asarray(tr.M[0], np.float64),
         # trajectory of the parameters at a few epochs (value handed to epoch k's analysis)
         "I_trace": np.asarray([tr.I[k] for k in meta["trace_epochs"]], np.float32),
+        # float(total_loss) of every epoch: what the early-stop test compares (SingleCore:211-219) -- the decision
+        # margin |loss - (best - tolerance)| of a run is computed from it (tests/test_gpu_parity.py)
+        "loss_trace": np.asarray(tr.loss, np.float32),
     }
+    assert rec["loss_trace"].size == len(tr.I), (rec["loss_trace"].size, len(tr.I))
     assert n == rec["I_last"].size
     return rec
 
@@ -93,7 +97,7 @@ def run_beamopt_case(seed=0):
     path = os.path.join(REFERENCE_DIR, "OpenPyStruct_BeamOpt.py")
     text = open(path).read()
     cut = text.index("# Plot loss history")
-    tr_I, tr_V, tr_M = [], [], []
+    tr_I, tr_V, tr_M, tr_loss = [], [], [], []
     real_analyze = opensees_shim.analyze
 
     def analyze(n=1):
@@ -109,7 +113,7 @@ def run_beamopt_case(seed=0):
     ns = {"__name__": "_reference_BO", "__file__": path}
     try:
         random.seed(seed)
-        with contextlib.redirect_stdout(io.StringIO()):
+        with contextlib.redirect_stdout(io.StringIO()), record_losses(tr_loss):
             exec(compile(text[:cut], path, "exec"), ns)
     finally:
         opensees_shim.analyze = real_analyze
@@ -117,7 +121,7 @@ def run_beamopt_case(seed=0):
     nn = ns["num_nodes"]
 
     class T:
-        I, V, M = tr_I, tr_V, tr_M
+        I, V, M, loss = tr_I, tr_V, tr_M, tr_loss
     result = {
         "I_values": ns["I_tensor"].detach().numpy().tolist(),
         "shear_forces": np.asarray(tr_V[-1], np.float32).tolist(),
@@ -155,6 +159,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "reference_goldens.npz"), **arrays)
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as fh:
         json.dump({"torch": torch.__version__, "numpy": np.__version__,
+                   # torch.sum's vector layout is ISA-dependent in principle (8-float AVX2 lanes assumed by the kernel's
+                   # summation order; SURVEY App. B found AVX2 / AVX512 / default builds bit-identical in practice)
+                   "cpu_capability": torch.backends.cpu.get_cpu_capability(),
                    "note": "reference source on oracle/opensees_shim.py; parity unpinned at the OpenSees boundary",
                    "cases": metas}, fh, indent=1)
     print(f"wrote {len(cases)} cases")

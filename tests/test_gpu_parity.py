@@ -10,8 +10,8 @@ import torch
 from oracle import c_oracle
 from openpystruct_b200 import _cabi, generator, ops, sampling
 from openpystruct_b200.params import BeamOptParams
-from tests.helpers import (goldens, golden_params, golden_case, oracle_params, oracle_run, rel_err,
-                           seeded_cases)
+from tests.helpers import (goldens, golden_decision_margin, golden_params, golden_case, oracle_params, oracle_run,
+                           oracle_run_mt, rel_err, seeded_cases)
 
 pytestmark = pytest.mark.gpu
 
@@ -32,11 +32,29 @@ def gpu_run(p, fixed, fn, fv, L):
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
-def assert_matches_oracle(a, b, flag=0):
-    """a = oracle, b = GPU."""
-    assert np.array_equal(a["status"], b["status"])
-    same = a["epochs"] == b["epochs"]
-    assert same.mean() >= (0.99 if flag == 0 else 0.97), (same.mean(), a["epochs"][~same], b["epochs"][~same])
+# "Identical early-stop decisions" (north_star), made testable: the stop test compares the fp32 loss with
+# best - tolerance (SingleCore:211); the oracle reports, per beam, how close the closest such comparison of the run
+# came to going the other way, in fp32 ulps of the loss (margin_ulps).  The loss of two correct implementations can
+# differ in the last bit (M, V differ at 1e-11 before the fp32 cast), so a stop epoch may differ ONLY on beams whose
+# margin is about one ulp -- everywhere else (>= 85 % of all beams) the decisions must be identical, and the beams
+# that do differ are bounded in number as well (measured on 40 000 beams: 0.01-0.03 % on the fixed bridge).
+MARGIN_ULPS = 2.0
+
+
+def assert_same_decisions(o, g, max_flip_rate):
+    """o = oracle, g = CUDA path; returns the mask of beams with identical stop epochs."""
+    assert np.array_equal(o["status"], g["status"])
+    flips = o["epochs"] != g["epochs"]
+    assert (o["margin_ulps"][flips] <= MARGIN_ULPS).all(), (np.flatnonzero(flips), o["margin_ulps"][flips],
+                                                            o["epochs"][flips], g["epochs"][flips])
+    assert flips.mean() <= max_flip_rate, (int(flips.sum()), flips.size)
+    return ~flips
+
+
+def assert_matches_oracle(a, b, flag=0, truth=None):
+    """a = FP64 oracle (the reference's banded-Cholesky arithmetic), b = CUDA path, truth = the same loop with the FE
+    solve in 80-bit arithmetic (needed on random bridges, whose ill-conditioned K makes FP64 Cholesky itself noisy)."""
+    same = assert_same_decisions(a, b, 0.002 if flag == 0 else 0.02)
     assert np.max(np.abs(a["I"][same] - b["I"][same]) / a["I"][same]) < 1e-5
     assert (a["I"][same] == b["I"][same]).mean() > 0.98
     assert rel_err(b["defl"][same, 0], a["defl"][same, 0]).max() < (1e-7 if flag == 0 else 1e-5)
@@ -44,6 +62,11 @@ def assert_matches_oracle(a, b, flag=0):
     assert rel_err(b["moment"][same, 0], a["moment"][same, 0]).max() < 1e-5
     assert rel_err(b["shear"][same, 0], a["shear"][same, 0]).max() < 1e-5
     assert (a["loss"][same] == b["loss"][same]).mean() > 0.98
+    if truth is not None:
+        st = assert_same_decisions(truth, b, 0.002)
+        assert np.max(np.abs(truth["I"][st] - b["I"][st]) / truth["I"][st]) < 1e-5
+        assert (truth["I"][st] == b["I"][st]).all(axis=1).mean() > 0.99
+        assert (truth["loss"][st] == b["loss"][st]).mean() > 0.99
 
 
 def test_library_sees_the_gpu():
@@ -66,40 +89,67 @@ def test_full_loop_against_c_oracle(script, flag, count, solver):
     p = BeamOptParams.for_script(script).replace(solver=solver)
     cases = seeded_cases(p, count, seed=101, flag=flag)
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
-    assert_matches_oracle(oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L), flag)
+    truth = oracle_run(p, fixed, fn, fv, L, 1) if (flag == 1 and solver != 1) else None
+    assert_matches_oracle(oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L), flag, truth)
 
 
 @pytest.mark.parametrize("solver", SOLVERS)
-def test_fixed_600_epochs_I_within_1e5(solver):
+@pytest.mark.parametrize("flag", [0, 1])
+def test_fixed_600_epochs_I_within_1e5(solver, flag):
+    """Optimised I within 1e-5 relative after a fixed epoch count, on ALL beams (no stop decision involved).
+    flag=1 (random bridges: short stiff spans, cond(K) up to 1e10): the tolerance is asserted against the loop with
+    the 80-bit FE solve; the reference's own FP64 banded Cholesky is further from that exact solve than the CUDA
+    path is, so against the FP64 oracle the bound is the FP64 oracle's own distance to the truth."""
     p = BeamOptParams.for_script("MC").replace(early_stop=False, solver=solver)
-    cases = seeded_cases(p, 256, seed=102)
+    cases = seeded_cases(p, 256, seed=102, flag=flag)
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
     a, b = oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L)
-    assert (b["epochs"] == 600).all()
-    assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
+    assert (b["epochs"] == 600).all() and not b["status"].any()
+    err64 = np.max(np.abs(a["I"] - b["I"]) / a["I"])
+    if flag == 0:
+        assert err64 < 1e-5
+    if flag == 1 or solver == 0:
+        t = oracle_run(p, fixed, fn, fv, L, 1)
+        err80 = np.max(np.abs(t["I"] - b["I"]) / t["I"])
+        own = np.max(np.abs(t["I"] - a["I"]) / t["I"])            # FP64 oracle against the 80-bit loop
+        if solver != 1:                                           # (solver 1 IS an FP64 band factorisation)
+            assert err80 < 1e-5, (err80, own)
+        assert err64 <= 2 * own + 1e-5 and err80 <= 2 * own + 1e-5, (err64, err80, own)
     assert (b["defl"][:, 0, -1] == 0).all() and (b["rot"][:, 0, -1] == 0).all()    # MultiCore:222-223
+
+
+# Reference runs whose stop epoch the CUDA path does not reproduce: torch's CPU sqrt (MKL VML) is not correctly
+# rounded on 0.74 % of its inputs (SURVEY finding 5), which moves the fp32 loss by one ulp now and then; on these two
+# runs (same beam: SC and MC scripts draw the same seed-0 stream) the reference's own closest decision was 0.7 ulp of
+# the loss away from going the other way (epoch 216) -- the IEEE-sqrt oracles (FP64 and 80-bit FE) both stop where
+# the CUDA path stops (232 / 268).  Every other run must stop on the reference's epoch.
+GOLDEN_FLIPS = {("SC", 0, 0): 232, ("MC", 0, 0): 268}
 
 
 @pytest.mark.parametrize("solver", SOLVERS)
 def test_reference_goldens_through_run_host(solver):
     """The committed reference runs (reference source + torch, made by tests/golden/make_golden.py)
     through the host-buffer C-ABI entry ops_beamopt_run_host."""
-    same = 0
+    flipped = {}
     for m, rec in goldens():
         p = golden_params(m).replace(solver=solver)
         fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, [golden_case(m)])
         out = _cabi.run_host(p, fixed, fn, fv, L, device=0)
         assert out["status"][0] == 0
+        key = (m["script"], m["seed"], m["flag"])
+        if out["epochs"][0] != m["epochs"]:
+            flipped[key] = int(out["epochs"][0])
+            margin, at = golden_decision_margin(m, rec)
+            assert margin < 1.0, (key, margin, at)            # the reference's own decision hung on the last bit
+            continue
         # I after a fixed number of epochs never depends on the stop decision: checked below; here the
-        # full early-stopped run (torch's non-IEEE MKL sqrt can move the stop of a minority of runs)
-        if out["epochs"][0] == m["epochs"]:
-            same += 1
-            assert np.max(np.abs(out["I"][0] - rec["I_values"]) / rec["I_values"]) < 1e-5
-            assert rel_err(out["moment"][0, 0], rec["bending_moments"]) < 1e-6
-            assert rel_err(out["shear"][0, 0], rec["shear_forces"]) < 1e-6
-            assert rel_err(out["defl"][0, 0], rec["deflections"]) < 1e-6
-            assert rel_err(out["rot"][0, 0], rec["rotations"]) < 1e-6
-    assert same >= 0.8 * len(goldens()), same
+        # full early-stopped run
+        assert np.max(np.abs(out["I"][0] - rec["I_values"]) / rec["I_values"]) < 1e-5
+        assert rel_err(out["moment"][0, 0], rec["bending_moments"]) < 1e-6
+        assert rel_err(out["shear"][0, 0], rec["shear_forces"]) < 1e-6
+        assert rel_err(out["defl"][0, 0], rec["deflections"]) < 1e-6
+        assert rel_err(out["rot"][0, 0], rec["rotations"]) < 1e-6
+    assert flipped == GOLDEN_FLIPS, flipped
 
 
 def test_reference_goldens_fixed_epoch_trajectory():
@@ -193,17 +243,24 @@ def test_empty_and_ragged_batches(solver):
 
 
 def test_beamopt_script_config_five_loads():
-    p = BeamOptParams.for_script("BO").replace(max_e=300)
+    """OpenPyStruct_BeamOpt.py's constants (5 rollers by rejection sampling, 5 loads, UDL -5000, tolerance 1e-2,
+    patience 10, num_epochs = 1000, BeamOpt:24-48): the early-stopped loop and all 1000 epochs with the stop off."""
+    p = BeamOptParams.for_script("BO")
+    assert p.max_e == 1000
     import random
     rng = random.Random(5)
     cases = []
-    while len(cases) < 16:
+    while len(cases) < 48:
         try:
             cases.append(sampling.sample_beamopt_case(rng=rng))
         except RuntimeError:
             pass
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
     assert_matches_oracle(oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L))
+    pf = p.replace(early_stop=False)
+    a, b = oracle_run_mt(pf, fixed, fn, fv, L), gpu_run(pf, fixed, fn, fv, L)
+    assert (b["epochs"] == 1000).all() and not b["status"].any()
+    assert np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
 
 
 @pytest.mark.parametrize("solver", SOLVERS)
@@ -317,6 +374,31 @@ def test_fine_discretisation_1000_elements(solver):
         assert rel_err(g[k], o80[k]).max() < 1e-9, k
 
 
+def test_fine_discretisation_full_length_runs():
+    """BASELINE config 5 at full length on 256 beams: the early-stopped loop (MultiCore constants) and 600 fixed
+    epochs of the production kernel for 1000 elements (one warp per beam).  cond(K) ~ 2e10 puts FP64 banded Cholesky
+    3e-8 away from the exact solve per analysis (SURVEY finding 10), so the oracle here is the loop with the 80-bit FE
+    solve: identical stop decisions (up to one-ulp margins) and I within 1e-5 on ALL beams after 600 epochs; the FP64
+    oracle is reported beside it with the bound "no further from the truth than twice the FP64 oracle itself"."""
+    p = BeamOptParams.for_script("MC").replace(num_nodes=1001)
+    cases = seeded_cases(p, 256, seed=32, roller_nodes=[100, 300, 700, 850, 1000])
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    t, g = oracle_run_mt(p, fixed, fn, fv, L, 1), gpu_run(p, fixed, fn, fv, L)
+    same = assert_same_decisions(t, g, 0.01)
+    assert np.max(np.abs(t["I"][same] - g["I"][same]) / t["I"][same]) < 1e-5
+    assert rel_err(g["moment"][same, 0], t["moment"][same, 0]).max() < 1e-6
+    assert rel_err(g["defl"][same, 0], t["defl"][same, 0]).max() < 1e-6
+    pf = p.replace(early_stop=False)
+    t, g = oracle_run_mt(pf, fixed, fn, fv, L, 1), gpu_run(pf, fixed, fn, fv, L)
+    o = oracle_run_mt(pf, fixed, fn, fv, L, 0)
+    assert (g["epochs"] == 600).all() and not g["status"].any()
+    err80 = np.max(np.abs(t["I"] - g["I"]) / t["I"])
+    own = np.max(np.abs(t["I"] - o["I"]) / t["I"])
+    err64 = np.max(np.abs(o["I"] - g["I"]) / o["I"])
+    assert err80 < 1e-5, (err80, own, err64)
+    assert err64 <= 2 * own + 1e-5, (err64, own)
+
+
 def test_session_matches_the_device_pointer_entry():
     """ops_beamopt_session_*: pinned host arrays in, pinned host arrays out, same bytes as ops_beamopt_launch;
     partial batches and reuse of one session."""
@@ -358,22 +440,21 @@ def test_shared_inertia_load_cases(num_cases):
     """BASELINE config 4 (extension): C load cases per beam share one I vector, summed
     energies; one record per (beam, case) with identical I_values."""
     p = BeamOptParams.for_script("MC").replace(num_cases=num_cases)
-    B = 96
+    B = 512
     cases = seeded_cases(p, B * num_cases, seed=107)
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases, num_cases)
-    a, b = oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L)
+    a, b = oracle_run_mt(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L)
     assert not b["status"].any()
-    same = a["epochs"] == b["epochs"]
-    assert same.mean() >= 0.98
+    same = assert_same_decisions(a, b, 0.01)
     assert np.max(np.abs(a["I"][same] - b["I"][same]) / a["I"][same]) < 1e-5
     assert (a["loss"][same] == b["loss"][same]).mean() > 0.95
     ns = int(same.sum())
     for key in ("defl", "rot", "moment", "shear"):
         assert rel_err(b[key][same].reshape(ns * num_cases, -1), a[key][same].reshape(ns * num_cases, -1)).max() < 1e-6, key
     # fixed epochs: I never depends on a stop decision
-    pf = p.replace(early_stop=False, max_e=120)
-    a, b = oracle_run(pf, fixed, fn, fv, L), gpu_run(pf, fixed, fn, fv, L)
-    assert (b["epochs"] == 120).all() and np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
+    pf = p.replace(early_stop=False)
+    a, b = oracle_run_mt(pf, fixed, fn, fv, L), gpu_run(pf, fixed, fn, fv, L)
+    assert (b["epochs"] == 600).all() and np.max(np.abs(a["I"] - b["I"]) / a["I"]) < 1e-5
     # host records: C consecutive records per beam, identical I_values (the trainers' reshape(total, n_cases, -1))
     rollers, avail = sampling.fixed_bridge(101)
     recs = generator.generate_samples_batched(range(6), 101, 0, 200.0, np.linspace(0, 200.0, 101), rollers, avail,
@@ -407,19 +488,24 @@ def test_columnar_dataset_and_trainer_preprocessing_on_device(tmp_path):
 def test_random_bridges_against_the_80bit_fe_loop():
     """flag=1 draws short, stiff spans whose K is ill conditioned: there the reference's FP64 banded
     Cholesky (the FP64 oracle) is itself several digits away from the exact solve.  Against the same loop
-    with the FE half in 80-bit arithmetic the CUDA path must be at least as close as the FP64 oracle is."""
+    with the FE half in 80-bit arithmetic the CUDA path makes identical stop decisions and is at least as
+    close as the FP64 oracle is; where it differs from the FP64 oracle, the FP64 oracle differs from the truth."""
     p = BeamOptParams.for_script("SC")
-    cases = seeded_cases(p, 1024, seed=2024, flag=1)
+    cases = seeded_cases(p, 2048, seed=2024, flag=1)
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
-    t = oracle_run(p, fixed, fn, fv, L, 1)
-    o = oracle_run(p, fixed, fn, fv, L, 0)
+    t = oracle_run_mt(p, fixed, fn, fv, L, 1)
+    o = oracle_run_mt(p, fixed, fn, fv, L, 0)
     g = gpu_run(p, fixed, fn, fv, L)
-    same_g, same_o = g["epochs"] == t["epochs"], o["epochs"] == t["epochs"]
-    assert (~same_g).sum() <= max((~same_o).sum(), 2)
+    same_g = assert_same_decisions(t, g, 0.002)
+    same_o = o["epochs"] == t["epochs"]
+    assert (~same_g).sum() <= (~same_o).sum()
+    # a stop epoch that differs from the reference arithmetic's is one the reference arithmetic gets "wrong" itself
+    assert ((g["epochs"] != o["epochs"]) <= (~same_o | ~same_g)).all()
     both = same_g & same_o
     err_g = np.max(np.abs(g["I"][both] - t["I"][both]) / t["I"][both])
     err_o = np.max(np.abs(o["I"][both] - t["I"][both]) / t["I"][both])
     assert err_g < 1e-5 and err_g <= 2 * err_o + 1e-7, (err_g, err_o)
+    assert (g["I"][same_g] == t["I"][same_g]).all(axis=1).mean() > 0.99
 
 
 @pytest.mark.parametrize("solver", [0, 3, 4])
@@ -434,8 +520,7 @@ def test_other_discretisations(num_nodes, solver):
     fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
     a, b = oracle_run(p, fixed, fn, fv, L), gpu_run(p, fixed, fn, fv, L)
     assert not b["status"].any()
-    same = a["epochs"] == b["epochs"]
-    assert same.mean() >= 0.99
+    same = assert_same_decisions(a, b, 0.01)
     assert np.max(np.abs(a["I"][same] - b["I"][same]) / a["I"][same]) < 1e-5
     assert (a["loss"][same] == b["loss"][same]).mean() > 0.95
     assert rel_err(b["moment"][same, 0], a["moment"][same, 0]).max() < 1e-6
