@@ -244,7 +244,8 @@ int ops_pipe_probe(int op, int iters, double *warp_inst_per_clk_per_sm, void *cu
  * Diagnostic (no reference counterpart): checks the branch-free fp32 division / square-root
  * sequences of the production kernel (csrc/fastmath.cuh) against the compiler's IEEE `/` and sqrtf
  * on `samples` random operands inside the ranges the kernel guarantees.  mismatches3 receives the
- * number of results that are not bit-identical {a/b, sqrt(x), 1/b}; rcp64_max_rel_err the largest
+ * number of results that are not bit-identical {a/b, sqrt(x), 1/b and the packed fp32 pair operations (FFMA2 / FMUL2 /
+ * FADD2 against the scalar instructions, incl. the product-then-sum that must stay un-fused)}; rcp64_max_rel_err the largest
  * |x * rcp64(x) - 1| of the FP64 reciprocal.  Synchronises the stream.
  */
 int ops_fastmath_selftest(int64_t samples, int64_t *mismatches3, int64_t *samples_run, double *rcp64_max_rel_err,

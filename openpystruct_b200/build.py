@@ -37,17 +37,37 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str = LIB_PATH, defines=(), sources=None) -> str:
+    """Compiles the translation units in parallel (one nvcc per .cu) and links them into ``out``.
+    ``defines``: extra -D macros (A/B variants of the kernels, loaded with OPS_B200_LIB)."""
+    if not force and out == LIB_PATH and not is_stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), flush=True)
-    subprocess.run(cmd, check=True)
-    return LIB_PATH
+    obj_dir = os.path.join(LIB_DIR, "obj_" + os.path.splitext(os.path.basename(out))[0])
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = nvcc_path()
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + [f"-D{d}" for d in defines]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        cmd = [nvcc, *flags, "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, sources or SOURCES))
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs], check=True)
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    # python -m openpystruct_b200.build [--force] [--out lib/variant.so] [-DNAME[=VALUE] ...]
+    _out = LIB_PATH
+    if "--out" in sys.argv:
+        _out = os.path.abspath(sys.argv[sys.argv.index("--out") + 1])
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv or _out != LIB_PATH, verbose="--quiet" not in sys.argv, out=_out, defines=_defs))

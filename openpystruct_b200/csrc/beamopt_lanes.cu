@@ -28,7 +28,10 @@ constexpr int LANES_MAX_THREADS = OPS_LANES_MAXT;
 // Many-round batches of the reference's discretisation: 12 warps per SM.  An iteration of a CTA costs a fixed
 // latency plus a part that grows with the resident warps (profiles/): 48 beams per SM and round beat 40 once a
 // batch runs several full rounds (+5 % at 6 rounds), while the 10 000-beam batch (1.7 rounds of 40) is faster at 320.
-constexpr int LANES_BIG_THREADS = 384;
+#ifndef OPS_LANES_BIGT
+#define OPS_LANES_BIGT 384
+#endif
+constexpr int LANES_BIG_THREADS = OPS_LANES_BIGT;
 constexpr int LANES_BIG_MIN_ROUNDS = 3;
 
 // synchronisation of the NC groups of a team: one warp (NC <= 4) or 8 NC / 32 whole warps (named barrier)
@@ -40,15 +43,13 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
     else asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "n"(NC * LPB) : "memory");
 }
 
-// Record of a beam (once per beam): fields of the last analysed inertias, then the last Adam step; SC instances then
-// copy the rows to the peers.  A macro because the kernel places it at two different points of the source (see the
-// note on code placement at the end of the kernel) and a lambda changes the code of the epoch loop.
+// Record of a beam (once per beam): fields of the last analysed inertias (parked by the beam's last pass), the
+// inertias after the last Adam step; SC instances then copy the rows to the peers.
 #define OPS_RECORD_PATH                                                                                              \
     {                                                                                                                \
         const bool fields = (t > 0) && (bad == 0);                                                                   \
         const long long row = p.row0 + b, rowc = row * NC + case_id; /* dataset rows of the beam / its load case */  \
         lane_emit_forces<EPL>(n, rg, ls, gs, fb.invLe, l, fields, p.shear + rowc * n, p.moment + rowc * n);          \
-        __syncwarp(gmask);                                                                                           \
         if (l == 0) {                                                                                                \
             LaneStore ls0 = ls;                                                                                      \
             group_emit_displacements(k, fb, ls0, gs, fields, p.defl + rowc * nn, p.rot + rowc * nn);                 \
@@ -58,7 +59,6 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
                 p.status[row] = bad;                                                                                 \
             }                                                                                                        \
         }                                                                                                            \
-        if (t > 0) lane_adam<EPL, false, NBK>(k, rg, ls, pc, neg_step, bc2_sqrt);                                         \
         if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + row * n);                                   \
         if (SC && p.dest.nd > 1) { /* dataset gather: every lane re-reads rows other lanes wrote */                  \
             __syncwarp(gmask);                                                                                       \
@@ -78,10 +78,7 @@ __global__ void __launch_bounds__(TFIX ? TFIX : LANES_MAX_THREADS, 1)
 beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // Slots per stage-major batch.  Five everywhere except the 320-thread scatter instance, whose epoch loop ptxas orders
-    // best with six (4.86-5.06 ms against 5.39-5.41 ms with five on 10 000 beams; the plain instances are 4-6 % slower
-    // with six): same arithmetic, same bits -- only the instruction order differs (profiles/r01_v6_ab_scatter.txt).
-    constexpr int NBK = (SC && TFIX == LANES_MAX_THREADS) ? 6 : lanes::NB;
+    constexpr int NBK = lanes::NBP;                                // slot pairs per stage-major batch
     const int T = TFIX ? TFIX : (int)blockDim.x, G = T / LPB;
     const int tid = threadIdx.x, l = tid & (LPB - 1), g = tid / LPB;
     const unsigned gmask = 0xffu << (tid & 24);
@@ -169,7 +166,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                 pc = pass1_consts(fb);
                 if (!bad) {
                     lane_init<EPL>(k, n, fb, gs, ls, l, rg);
-                    lane_pass1<EPL>(rg, ls, pc);
+                    lane_pass1<EPL>(rg, ls, pc, false);
                 } else {
                     lane_reset<EPL>(k, rg);
                 }
@@ -199,7 +196,9 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             if (NC * LPB <= 32) __syncwarp();
             else if (run) team_sync<NC>(team_mask, barrier_id);    // whole warps belong to one team: uniform
         }
-        if (run) lane_forces<EPL, NC, NBK>(k, n, rg, ls, gs, fb.invLe, l, case_id);
+        // this epoch may be the beam's last: the pass parks the inertias it starts from for the record
+        const bool stage_I = run && ((t + 1 >= k.max_epochs) || (k.early_stop && counter + 1 >= k.patience));
+        if (run) lane_pass<EPL, NC, NBK>(k, n, rg, ls, gs, pc, fb.invLe, l, case_id, neg_step, bc2_sqrt, stage_I);
         if (NC * LPB <= 32) __syncwarp();                           // (NC > 1: exchange columns are rewritten next epoch)
         else if (run) team_sync<NC>(team_mask, barrier_id);
         if (run) {
@@ -213,23 +212,10 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             }
             if (t >= k.max_epochs) done = true;
         }
-        // Code placement follows source order, and it matters by 3-5 % although the epoch loop's instructions are the
-        // same (profiles/r01_v6_ab_scatter.txt): with the Adam step directly behind the loss the loop is one contiguous
-        // 48 KB range -- best for many-round batches (384-thread instance, +2.6 % on 1 M beams) and no worse for the
-        // scatter instances; the 320-thread instance that runs 10 000 beams in 1.7 rounds is 4 % faster with the
-        // record path between the loss and the Adam step.
-        constexpr bool ADAM_FIRST = SC || TFIX == LANES_BIG_THREADS;
-        if (ADAM_FIRST) {
-            if (have && !done) lane_adam<EPL, true, NBK>(k, rg, ls, pc, neg_step, bc2_sqrt);     // + PASS 1 of the next epoch
-            if (have && done) {
-                OPS_RECORD_PATH
-            }
-        } else if (have) {
-            if (!done) {
-                lane_adam<EPL, true, NBK>(k, rg, ls, pc, neg_step, bc2_sqrt);
-            } else {
-                OPS_RECORD_PATH
-            }
+        if (have && done) {
+            OPS_RECORD_PATH
+        } else if (stage_I) {
+            lane_pass1<EPL>(rg, ls, pc, true);                      // the beam goes on: the sums the parked inertias displaced
         }
     }
 }
@@ -296,6 +282,16 @@ static cudaError_t launch_instance(const BeamConsts &k, long long B, const OptPt
 // instances with the in-kernel dataset gather: every single-case instance, and the 13-slot multi-case ones
 bool lanes_scatter_supported(const LanesPlan &pl) { return pl.num_cases == 1 || pl.epl == 13; }
 
+#ifdef OPS_LANES_DEV
+// development build (kernel iteration on the reference's discretisation only: compiles in a fraction of the time)
+cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream)
+{
+    if (pl.num_cases != 1 || pl.nfix != 100 || p.dest.nd > 1) return cudaErrorInvalidValue;
+    if (pl.threads == LANES_MAX_THREADS) return launch_instance<13, 100, 1, LANES_MAX_THREADS, false>(k, B, p, pl, stream);
+    if (pl.threads == LANES_BIG_THREADS) return launch_instance<13, 100, 1, LANES_BIG_THREADS, false>(k, B, p, pl, stream);
+    return launch_instance<13, 100, 1, 0, false>(k, B, p, pl, stream);
+}
+#else
 template <bool SC>
 static cudaError_t launch_single_case(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl,
                                       cudaStream_t stream)
@@ -334,6 +330,7 @@ cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, con
     }
     return sc ? launch_single_case<true>(k, B, p, pl, stream) : launch_single_case<false>(k, B, p, pl, stream);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // self test of fastmath.cuh against the compiler's IEEE operators (ops_fastmath_selftest)
@@ -378,6 +375,23 @@ __global__ void fastmath_selftest_kernel(int per_thread, unsigned long long seed
         worst = e > worst ? e : worst;
         const double e0 = fabs(fm::rcp64_a(xd) * xd - 1.0);          // the bare MUFU.RCP64H seed
         worst_seed = e0 > worst_seed ? e0 : worst_seed;
+        // packed fp32 pairs (FFMA2 / FMUL2 / FADD2, fastmath.cuh): each half must carry the bits of the scalar operation,
+        // and the un-fused product-then-sum must not have been contracted
+        {
+            const fm::F2 pa = fm::f2(a, -x), pb = fm::f2(b, qi), pc = fm::f2(x, a);
+            const fm::F2 f = fm::fma2(pa, pb, pc), m2 = fm::mul2(pa, pb), s2 = fm::add2(pa, pc), ma = fm::mul2_add(pa, pb, pc);
+            const fm::F2 fn = fm::fma2(fm::neg2(pa), pb, fm::splat(1.0f));
+            bad_rsq += __float_as_uint(f.x) != __float_as_uint(fmaf(pa.x, pb.x, pc.x));
+            bad_rsq += __float_as_uint(f.y) != __float_as_uint(fmaf(pa.y, pb.y, pc.y));
+            bad_rsq += __float_as_uint(m2.x) != __float_as_uint(pa.x * pb.x);
+            bad_rsq += __float_as_uint(m2.y) != __float_as_uint(pa.y * pb.y);
+            bad_rsq += __float_as_uint(s2.x) != __float_as_uint(pa.x + pc.x);
+            bad_rsq += __float_as_uint(s2.y) != __float_as_uint(pa.y + pc.y);
+            bad_rsq += __float_as_uint(ma.x) != __float_as_uint(__fadd_rn(__fmul_rn(pa.x, pb.x), pc.x));
+            bad_rsq += __float_as_uint(ma.y) != __float_as_uint(__fadd_rn(__fmul_rn(pa.y, pb.y), pc.y));
+            bad_rsq += __float_as_uint(fn.x) != __float_as_uint(fmaf(-pa.x, pb.x, 1.0f));
+            bad_rsq += __float_as_uint(fn.y) != __float_as_uint(fmaf(-pa.y, pb.y, 1.0f));
+        }
     }
     atomicAdd(out + 0, bad_div);
     atomicAdd(out + 1, bad_sqrt);

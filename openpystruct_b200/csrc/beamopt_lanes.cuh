@@ -7,8 +7,9 @@
 // Mapping.  Lane l of a beam's 8-lane group owns the elements e = 8 k + l, k = 0..EPL-1: lane l is
 // SIMD lane l of the 8-float vectors ATen's cascade_sum works on, so torch.sum's summation order
 // (beamopt_core.cuh, torch_sum_f32) falls out of per-lane running sums plus one fixed-order combine.
-// Per element the lane keeps I, Adam's m and v, the gradient and the element's index inside its span
-// in REGISTERS; the I-independent statics of the element ({M0, Q0} of the simply supported span) sit in
+// Per element the lane keeps I, Adam's m and v in REGISTERS -- as PAIRS of consecutive slots (2 j, 2 j + 1), the
+// operands of sm_100a's packed fp32 instructions (fastmath.cuh) -- plus one byte for the element's index inside
+// its span; the I-independent statics of the element ({M0, Q0} of the simply supported span) sit in
 // shared memory, one conflict-free [slot][thread] column per lane, and the flexibility weights are
 // derived from them on the fly (G = 6 M0 + 3 Le Q0 + const, g1 x1 + g2 x2 = d (G ke + g2)), which is what
 // lets 40+ beams stay resident per SM.
@@ -21,10 +22,13 @@
 // (g1 = 2 M0 + m2 - w Le^2/4, g2 = 2 m2 + M0 - w Le^2/4 from the simply supported moment diagram M0 of
 // the span, x1 = ke d, x2 = x1 + d; the common factor Le / (6 E) of the flexibilities cancels in the
 // support-moment system and is only applied for the displacements).  Each lane accumulates the five
-// sums over its own elements (PASS 1), the group reduces them through shared memory in a fixed
-// order, every lane solves the <= 4-unknown tridiagonal system redundantly, and PASS 2 evaluates
+// sums over its own elements, the group reduces them through shared memory in a fixed
+// order, every lane solves the <= 4-unknown tridiagonal system redundantly, and ONE PASS over the lane's
+// elements (lane_pass) evaluates
 //     Mc_e = M0_e + MS_l + (MS_r - MS_l) d ke ,   V_e = Q0_e + (MS_r - MS_l) d / Le
-// followed by the fp32 loss terms, the frozen-M,V gradient and the Adam update of its elements.
+// followed by the fp32 loss terms, the frozen-M,V gradient, the Adam update of its elements and the five sums of
+// the NEXT epoch on the updated inertias -- {M0, Q0} and ke are fetched once per element and epoch, and neither
+// the gradient nor anything else per element survives the pass.
 //
 // Load cases sharing one inertia vector (not in the reference): the NC cases of a beam
 // run on NC adjacent groups (a "team").  Every group carries the same I, m, v and the coefficients of its
@@ -59,10 +63,21 @@ OPS_HD constexpr int lane_doubles(int epl, int nc) { return 2 * epl + SCR_SLOTS 
 
 template <int EPL>
 struct LaneRegs {
-    float I[EPL], m[EPL], v[EPL], g[EPL], ke[EPL];
-    unsigned long long spans;                   // 3 bits per slot k: span id of element 8 k + l
+    static constexpr int NP = (EPL + 1) / 2;    // slot pairs; an odd EPL leaves one padding slot (kk = EPL)
+    fm::F2 I[NP], m[NP], v[NP];                 // pair j = slots 2 j, 2 j + 1
+    unsigned int ke[(2 * NP + 3) / 4];          // one byte per slot: index of the element inside its span (<= 167)
+    unsigned long long spans;                   // 3 bits per slot k < EPL: span id of element 8 k + l
     unsigned int starts, ends;                  // bit k: slot k opens / closes a run of slots of one (real) span
 };
+
+// element index inside its span of slot kk as a double (I2F.F64.U8 with a byte selector: one conversion)
+template <int EPL>
+OPS_HD double slot_ke(const LaneRegs<EPL> &rg, int kk)
+{
+    return (double)((rg.ke[kk >> 2] >> (8 * (kk & 3))) & 0xffu);
+}
+template <int EPL>
+OPS_HD float &slot_ref(fm::F2 (&a)[LaneRegs<EPL>::NP], int kk) { return (kk & 1) ? a[kk >> 1].y : a[kk >> 1].x; }
 
 struct alignas(16) Pair {                       // two doubles moved with one 128-bit shared access
     double x, y;
@@ -147,16 +162,20 @@ template <int EPL>
 OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const GroupStore &gs, const LaneStore &ls,
                       int l, LaneRegs<EPL> &rg)
 {
+    constexpr int NP = LaneRegs<EPL>::NP;
     const int m = fb.m, last = fb.last, nl = fb.nloads;
     for (int s = 0; s < SCR_SLOTS; ++s) ls.scr[(long)s * ls.ls] = 0.0;
     unsigned long long spans = 0;
     unsigned int starts = 0, ends = 0;
     int prev = -1;
 #pragma unroll
+    for (int w = 0; w < (2 * NP + 3) / 4; ++w) rg.ke[w] = 0u;
+#pragma unroll
     for (int kk = 0; kk < EPL; ++kk) {
         const int e = LPB * kk + l;
         int sp = DUMMY;
-        double kef = 0.0, M0 = 0.0, Q0 = 0.0;
+        int kei = 0;
+        double M0 = 0.0, Q0 = 0.0;
         float I0 = 1.0f;                        // padding slots: harmless inertia, never read back
         if (e < n) {
             I0 = k.I0f;
@@ -176,7 +195,7 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
                         Ms = fma(P, (double)(e - nd) * fb.Le, Ms);
                     }
                 }
-                sp = j; kef = ke; M0 = Ms; Q0 = Qs;
+                sp = j; kei = e - na; M0 = Ms; Q0 = Qs;
             } else {
                 const double r = (double)(n - e);
                 double Ms = fb.wl2h * (r * r), Qs = fb.wl * r;
@@ -197,10 +216,12 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
             if (kk > 0 && prev != DUMMY) ends |= 1u << (kk - 1);
         }
         prev = sp;
-        rg.I[kk] = I0; rg.m[kk] = 0.0f; rg.v[kk] = 0.0f; rg.g[kk] = 0.0f; rg.ke[kk] = (float)kef;
+        slot_ref<EPL>(rg.I, kk) = I0; slot_ref<EPL>(rg.m, kk) = 0.0f; slot_ref<EPL>(rg.v, kk) = 0.0f;
+        rg.ke[kk >> 2] |= (unsigned int)kei << (8 * (kk & 3));
         Pair mq; mq.x = M0; mq.y = Q0;
         ls.mq[(long)kk * ls.ls] = mq;
     }
+    if (EPL & 1) { rg.I[NP - 1].y = 1.0f; rg.m[NP - 1].y = 0.0f; rg.v[NP - 1].y = 0.0f; }     // the pair's padding half
     if (prev != DUMMY) ends |= 1u << (EPL - 1);
     rg.spans = spans; rg.starts = starts; rg.ends = ends;
 }
@@ -209,10 +230,11 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
 template <int EPL>
 OPS_HD void lane_reset(const BeamConsts &k, LaneRegs<EPL> &rg)
 {
+    constexpr int NP = LaneRegs<EPL>::NP;
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) {
-        rg.I[kk] = k.I0f; rg.m[kk] = 0.0f; rg.v[kk] = 0.0f; rg.g[kk] = 0.0f; rg.ke[kk] = 0.0f;
-    }
+    for (int j = 0; j < NP; ++j) { rg.I[j] = fm::splat(k.I0f); rg.m[j] = fm::splat(0.0f); rg.v[j] = fm::splat(0.0f); }
+#pragma unroll
+    for (int w = 0; w < (2 * NP + 3) / 4; ++w) rg.ke[w] = 0u;
     rg.spans = 0; rg.starts = 0; rg.ends = 0;
 }
 
@@ -244,13 +266,12 @@ OPS_HD Pass1Consts pass1_consts(const FlexBeam &fb)
     return c;
 }
 
+// one element's contribution to the running sums; `store`: finished partials go to the lane's scratch column
 template <int EPL>
 OPS_HD void pass1_accumulate(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, int kk, double r,
-                             SpanSums &a)
+                             double ke, const Pair &mq, bool store, SpanSums &a)
 {
     const double keep = ((rg.starts >> kk) & 1u) ? 0.0 : 1.0;
-    const double ke = (double)rg.ke[kk];
-    const Pair mq = ls.mq[(long)kk * ls.ls];
     const double G = fma(6.0, mq.x, fma(pc.k3Le, mq.y, pc.cG));
     const double g2 = fma(3.0, mq.x, fma(pc.k2Le, mq.y, pc.cg2));
     const double t = r * ke;
@@ -259,19 +280,29 @@ OPS_HD void pass1_accumulate(const LaneRegs<EPL> &rg, const LaneStore &ls, const
     a.R2 = fma(t, ke, a.R2 * keep);
     a.G = fma(r, G, a.G * keep);
     a.Q = fma(r, fma(G, ke, g2), a.Q * keep);
-    if ((rg.ends >> kk) & 1u) {
+    if (((rg.ends >> kk) & 1u) && store) {
         const int j = (int)((rg.spans >> (3 * kk)) & 7u);
         double *s = ls.scr + (long)(j * NSUM) * ls.ls;
         s[0] = a.R0; s[ls.ls] = a.R1; s[2 * ls.ls] = a.R2; s[3 * ls.ls] = a.G; s[4 * ls.ls] = a.Q;
     }
 }
 
+// the sums on their own: first epoch of a beam (parked = false), and after an epoch whose pass parked the inertias
+// in the first slots of the scratch column instead (those slots are cleared first: a lane only ever writes the
+// partials of the spans it touches, the others must read zero)
 template <int EPL>
-OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc)
+OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, bool parked)
 {
+    if (parked) {
+#pragma unroll
+        for (int j = 0; j < LaneRegs<EPL>::NP; ++j) ls.scr[(long)j * ls.ls] = 0.0;
+    }
     SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) pass1_accumulate<EPL>(rg, ls, pc, kk, fm::rcp64((double)rg.I[kk]), a);
+    for (int kk = 0; kk < EPL; ++kk) {
+        const float If = (kk & 1) ? rg.I[kk >> 1].y : rg.I[kk >> 1].x;
+        pass1_accumulate<EPL>(rg, ls, pc, kk, fm::rcp64((double)If), slot_ke<EPL>(rg, kk), ls.mq[(long)kk * ls.ls], true, a);
+    }
 }
 
 // Group reduction of the partials and the flexibility coefficients of the span: lane j < NSPAN adds
@@ -373,20 +404,21 @@ OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const G
 {
     const Pair lo = table_row(gs.tab, row_offset(rg.spans, kk));
     const Pair mq = ls.mq[(long)kk * ls.ls];
-    Mc = fma(lo.y, (double)rg.ke[kk], mq.x + lo.x);
+    Mc = fma(lo.y, slot_ke<EPL>(rg, kk), mq.x + lo.x);
     Qv = fma(lo.y, invLe, mq.y);
 }
 
-// Elements are processed in batches of NB slots, STAGE BY STAGE across the batch: the stages of one
-// element are a ~150-cycle dependent chain (MUFU -> Newton -> quotient -> ...), and written element
-// by element ptxas leaves the chains serial at this register budget; stage-major order puts NB
-// independent instructions between dependent ones.
-#ifndef OPS_LANES_NB
-#define OPS_LANES_NB 5
+// Slots are processed in batches of NBP PAIRS, STAGE BY STAGE across the batch: the stages of one element are a
+// ~150-cycle dependent chain (MUFU -> Newton -> quotient -> ...), and written element by element ptxas leaves the
+// chains serial at this register budget; stage-major order puts the batch's independent instructions between
+// dependent ones.  A packed fp32 instruction occupies the FMA pipe for two cycles, so two pairs per stage already
+// cover its four-cycle latency.
+#ifndef OPS_LANES_NBP
+#define OPS_LANES_NBP 3
 #endif
-constexpr int NB = OPS_LANES_NB;
+constexpr int NBP = OPS_LANES_NBP;
 
-// multi-case kernels, before PASS 2: M^2, V^2 of this group's load case into the exchange column
+// multi-case kernels, before the pass: M^2, V^2 of this group's load case into the exchange column
 template <int EPL>
 OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe)
 {
@@ -401,108 +433,194 @@ OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, cons
     }
 }
 
-// PASS 2: end forces, loss terms d, q and autograd's gradient with M, V constant (element_update_f32,
-// first half; the gradient is kept in rg.g), torch.sum partials of sum I, sum d, sum q.
-// NC > 1: the squares come from the exchange columns of the team (case_id = this group's case).
-// fp32 ranges for the branch-free division / square root: I in [clamp_min, 1e20) (the clamp,
-// SingleCore:208), c = M^2 and h = V^2 zero or >= 2^-100.
-template <int EPL, int NC, int NBX = NB>
-OPS_HD void lane_forces(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe,
-                        int l, int case_id)
+// torch.sum partials of one quantity: the four ILP rows as two packed pairs {row 0, row 1}, {row 2, row 3}, and the
+// scalar tail.  Pair j = slots 2 j, 2 j + 1 falls on rows (0, 1) or (2, 3) of the 4-row block, so inside the block
+// one packed add per pair keeps every row's own summation order.
+struct SumAcc {
+    fm::F2 r01, r23;
+    float tail;
+};
+OPS_HD void sum_slot(SumAcc &a, const SumShape &sh, int kk, int l, float x)
 {
-    constexpr int NB = NBX;                     // slots per batch of this instance (shadows the default)
+    if (kk < sh.blk) {
+        const int r = kk & 3;
+        if (r == 0) a.r01.x += x; else if (r == 1) a.r01.y += x; else if (r == 2) a.r23.x += x; else a.r23.y += x;
+    } else if (kk < sh.vec) {
+        a.r01.x += x;
+    } else if (kk == sh.vec && l < sh.ntail) {
+        a.tail = x;
+    }
+}
+template <int EPL>
+OPS_HD void sum_pair(SumAcc &a, const SumShape &sh, int j, int l, fm::F2 x)
+{
+    if (2 * j + 1 < sh.blk) {
+        if (j & 1) a.r23 = fm::add2(a.r23, x); else a.r01 = fm::add2(a.r01, x);
+    } else {
+        sum_slot(a, sh, 2 * j, l, x.x);
+        if (2 * j + 1 < EPL) sum_slot(a, sh, 2 * j + 1, l, x.y);
+    }
+}
+OPS_HD float sum_rows(const SumAcc &a) { return ((a.r01.x + a.r01.y) + a.r23.x) + a.r23.y; }
+
+// THE PASS over the lane's elements, once per epoch: end forces from the span table, loss terms d, q and autograd's
+// gradient with M, V constant (element_update_f32, first half), torch.sum partials of sum I, sum d, sum q; then --
+// the record of a beam needs nothing of the step but the new I, and the step is taken whether or not this epoch
+// turns out to be the beam's last (SingleCore:202-208 come before the stop test :211-219) -- the Adam step + clamp
+// on the lane's elements (second half) and the flexibility sums of the NEXT epoch on the updated inertias.
+// NC > 1: the squares come from the exchange columns of the team (case_id = this group's case).
+//
+// stage_I: this epoch may be the beam's last (the caller knows: epoch count, patience counter), so the inertias the
+// forces were computed FROM -- the record's displacements integrate them -- are parked in the scratch column, in
+// place of the next epoch's partial sums; if the beam goes on after all, the caller redoes the sums (lane_pass1).
+// fp32 ranges for the branch-free division / square root: I in [clamp_min, 1e20) (the clamp, SingleCore:208),
+// c = M^2 and h = V^2 zero or >= 2^-100.  The fast square root of Adam's v needs v >= 2^-101; v is an EMA of g^2, so
+// anything smaller means g vanished on every epoch so far -- tested per batch, with the generic operators as the
+// (cold) alternative.
+template <int EPL, int NC, int NBX = NBP>
+OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs,
+                      const Pass1Consts &pc, double invLe, int l, int case_id, float neg_step, float bc2_sqrt, bool stage_I)
+{
+    using fm::F2; using fm::splat; using fm::neg2; using fm::mul2; using fm::add2; using fm::fma2;
+    constexpr int NB = NBX;                     // pairs per batch of this instance
+    constexpr int NP = LaneRegs<EPL>::NP;
     const SumShape sh = sum_shape(n);
-    float aI[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ad[4] = {0.0f, 0.0f, 0.0f, 0.0f}, aq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    float tI = 0.0f, td = 0.0f, tq = 0.0f;
+    SumAcc aI = {splat(0.0f), splat(0.0f), 0.0f}, ad = aI, aq = aI;
+    SpanSums acc = {0.0, 0.0, 0.0, 0.0, 0.0};
     const PairF *x0 = ls.xc - (long)case_id * LPB;             // this lane's column in the team's case-0 group
-    // one operation per stage across the batch (OPS_B: "for every live slot i of the batch"); the fast-path
-    // sequences of fastmath.cuh are written out step by step so that consecutive instructions are independent
-#define OPS_B _Pragma("unroll") for (int i = 0; i < NB; ++i) if (k0 + i < EPL)
+    const F2 one = splat(1.0f), half = splat(0.5f);
+    const float rbc = fm::rcp_r(bc2_sqrt);
+    // one operation per stage across the batch (OPS_P: "for every live pair i of the batch", OPS_S: "for every live
+    // slot s of the batch", slot kk = 2 p0 + s); the fast-path sequences of fastmath.cuh are written out step by
+    // step so that consecutive instructions are independent
+#define OPS_P _Pragma("unroll") for (int i = 0; i < NB; ++i) if (p0 + i < NP)
+#define OPS_S _Pragma("unroll") for (int s_ = 0; s_ < 2 * NB; ++s_) if (2 * p0 + s_ < EPL)
 #pragma unroll
-    for (int k0 = 0; k0 < EPL; k0 += NB) {
-        float I[NB], c[NB], h[NB], b[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB];
-        float t0[NB], t1[NB], t2[NB];
-        OPS_B I[i] = rg.I[k0 + i];
+    for (int p0 = 0; p0 < NP; p0 += NB) {
+        F2 I[NB], c[NB], h[NB], nb[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB], g[NB];
+        F2 t0[NB], t1[NB], t2[NB];
+        Pair mq[2 * NB];
+        double ke[2 * NB];
+        OPS_P I[i] = rg.I[p0 + i];
         if (NC == 1) {
-            Pair lo[NB], mq[NB];
-            double ke[NB], Mc[NB], Qv[NB];
-            OPS_B {
-                lo[i] = table_row(gs.tab, row_offset(rg.spans, k0 + i));
-                mq[i] = ls.mq[(long)(k0 + i) * ls.ls];
-                ke[i] = (double)rg.ke[k0 + i];
-            }
-            OPS_B { Mc[i] = mq[i].x + lo[i].x; Qv[i] = fma(lo[i].y, invLe, mq[i].y); }
-            OPS_B Mc[i] = fma(lo[i].y, ke[i], Mc[i]);
-            OPS_B { c[i] = (float)Mc[i]; h[i] = (float)Qv[i]; }
-            OPS_B { c[i] = c[i] * c[i]; h[i] = h[i] * h[i]; }
-        } else {
-            OPS_B {
-                PairF x = x0[(long)(k0 + i) * ls.ls];
-                c[i] = x.c; h[i] = x.h;
+            Pair lo[2 * NB];
+            double Mc[2 * NB], Qv[2 * NB];
 #pragma unroll
-                for (int cc = 1; cc < NC; ++cc) {
-                    x = x0[(long)(k0 + i) * ls.ls + cc * LPB];
-                    c[i] += x.c; h[i] += x.h;
+            for (int s_ = 0; s_ < 2 * NB; ++s_) { Mc[s_] = 0.0; Qv[s_] = 0.0; }      // (the padding half of an odd EPL)
+            OPS_S {
+                lo[s_] = table_row(gs.tab, row_offset(rg.spans, 2 * p0 + s_));
+                mq[s_] = ls.mq[(long)(2 * p0 + s_) * ls.ls];
+                ke[s_] = slot_ke<EPL>(rg, 2 * p0 + s_);
+            }
+            OPS_S { Mc[s_] = mq[s_].x + lo[s_].x; Qv[s_] = fma(lo[s_].y, invLe, mq[s_].y); }
+            OPS_S Mc[s_] = fma(lo[s_].y, ke[s_], Mc[s_]);
+            OPS_P { c[i] = fm::f2((float)Mc[2 * i], (float)Mc[2 * i + 1]); h[i] = fm::f2((float)Qv[2 * i], (float)Qv[2 * i + 1]); }
+            OPS_P { c[i] = mul2(c[i], c[i]); h[i] = mul2(h[i], h[i]); }
+        } else {
+            OPS_P {
+                c[i] = splat(0.0f); h[i] = splat(0.0f);
+#pragma unroll
+                for (int hs = 0; hs < 2; ++hs) {
+                    const int kk = 2 * (p0 + i) + hs;
+                    if (kk < EPL) {
+                        PairF x = x0[(long)kk * ls.ls];
+                        float cs = x.c, hq = x.h;
+#pragma unroll
+                        for (int cc = 1; cc < NC; ++cc) {
+                            x = x0[(long)kk * ls.ls + cc * LPB];
+                            cs += x.c; hq += x.h;
+                        }
+                        if (hs) { c[i].y = cs; h[i].y = hq; } else { c[i].x = cs; h[i].x = hq; }
+                    }
                 }
             }
         }
-        OPS_B { b[i] = k.E2 * I[i]; y[i] = fm::rsq_a(I[i]); }
-        OPS_B b[i] = b[i] + k.epsf;
+        // nb = -(2E I + eps) ; y ~ 1 / sqrt(I)
+        OPS_P { nb[i] = fm::mul2_add(I[i], splat(-k.E2), splat(-k.epsf)); y[i] = fm::rsq2_a(I[i]); }
         // rb = refined 1 / b ; s = sqrt(I)
-        OPS_B { rb[i] = fm::rcp_a(b[i]); t0[i] = I[i] * y[i]; y[i] = y[i] * 0.5f; }
-#if defined(__CUDA_ARCH__)
-        OPS_B { t1[i] = fmaf(-b[i], rb[i], 1.0f); t2[i] = fmaf(-t0[i], t0[i], I[i]); }
-        OPS_B { rb[i] = fmaf(rb[i], t1[i], rb[i]); s[i] = fmaf(t2[i], y[i], t0[i]); }
+        OPS_P { rb[i] = fm::rcp2_a(neg2(nb[i])); t0[i] = mul2(I[i], y[i]); y[i] = mul2(y[i], half); }
+        OPS_P { t1[i] = fma2(nb[i], rb[i], one); t2[i] = fma2(neg2(t0[i]), t0[i], I[i]); }
+        OPS_P { rb[i] = fma2(rb[i], t1[i], rb[i]); s[i] = fma2(t2[i], y[i], t0[i]); }
         // d = c / b ; gg = Gf (kf s) ; rs = 1 / s
-        OPS_B { t0[i] = c[i] * rb[i]; gg[i] = k.kf * s[i]; rs[i] = fm::rcp_a(s[i]); }
-        OPS_B { t1[i] = fmaf(-b[i], t0[i], c[i]); gg[i] = k.Gf * gg[i]; t2[i] = fmaf(-s[i], rs[i], 1.0f); }
-        OPS_B { d[i] = fmaf(rb[i], t1[i], t0[i]); rgg[i] = fm::rcp_a(gg[i]); rs[i] = fmaf(rs[i], t2[i], rs[i]); }
+        OPS_P { t0[i] = mul2(c[i], rb[i]); gg[i] = mul2(splat(k.kf), s[i]); rs[i] = fm::rcp2_a(s[i]); }
+        OPS_P { t1[i] = fma2(nb[i], t0[i], c[i]); gg[i] = mul2(splat(k.Gf), gg[i]); t2[i] = fma2(neg2(s[i]), rs[i], one); }
+        OPS_P { d[i] = fma2(rb[i], t1[i], t0[i]); rgg[i] = fm::rcp2_a(gg[i]); rs[i] = fma2(rs[i], t2[i], rs[i]); }
         // db = d / b ; rgg = refined 1 / gg ; rs = RN(1 / s)
-        OPS_B { t0[i] = d[i] * rb[i]; t1[i] = fmaf(-gg[i], rgg[i], 1.0f); t2[i] = fmaf(-s[i], rs[i], 1.0f); }
-        OPS_B { db[i] = fmaf(-b[i], t0[i], d[i]); rgg[i] = fmaf(rgg[i], t1[i], rgg[i]); rs[i] = fmaf(rs[i], t2[i], rs[i]); }
-        OPS_B { db[i] = fmaf(rb[i], db[i], t0[i]); t1[i] = h[i] * rgg[i]; rs[i] = 0.5f * rs[i]; }
+        OPS_P { t0[i] = mul2(d[i], rb[i]); t1[i] = fma2(neg2(gg[i]), rgg[i], one); t2[i] = fma2(neg2(s[i]), rs[i], one); }
+        OPS_P { db[i] = fma2(nb[i], t0[i], d[i]); rgg[i] = fma2(rgg[i], t1[i], rgg[i]); rs[i] = fma2(rs[i], t2[i], rs[i]); }
+        OPS_P { db[i] = fma2(rb[i], db[i], t0[i]); t1[i] = mul2(h[i], rgg[i]); rs[i] = mul2(half, rs[i]); }
         // q = h / gg ; bending branch gb = ((-am) db) E2
-        OPS_B { db[i] = (-k.am) * db[i]; t2[i] = fmaf(-gg[i], t1[i], h[i]); }
-        OPS_B { db[i] = db[i] * k.E2; q[i] = fmaf(rgg[i], t2[i], t1[i]); }
+        OPS_P { db[i] = mul2(splat(-k.am), db[i]); t2[i] = fma2(neg2(gg[i]), t1[i], h[i]); }
+        OPS_P { db[i] = mul2(db[i], splat(k.E2)); q[i] = fma2(rgg[i], t2[i], t1[i]); }
         // qg = q / gg
-        OPS_B t0[i] = q[i] * rgg[i];
-        OPS_B t1[i] = fmaf(-gg[i], t0[i], q[i]);
-        OPS_B qg[i] = fmaf(rgg[i], t1[i], t0[i]);
-#else
-        OPS_B {
-            s[i] = sqrtf(I[i]);
-            d[i] = c[i] / b[i];
-            db[i] = ((-k.am) * (d[i] / b[i])) * k.E2;
-            gg[i] = k.Gf * (k.kf * s[i]);
-            q[i] = h[i] / gg[i];
-            qg[i] = q[i] / gg[i];
-            rs[i] = 0.5f * (1.0f / s[i]);
+        OPS_P t0[i] = mul2(q[i], rgg[i]);
+        OPS_P t1[i] = fma2(neg2(gg[i]), t0[i], q[i]);
+        OPS_P qg[i] = fma2(rgg[i], t1[i], t0[i]);
+        // shear branch gs = ((((-as) qg) Gf) kf) (0.5 / s) ; g = (1 + gs) + gb  (sums of products: scalar adds, fastmath.cuh)
+        OPS_P qg[i] = mul2(splat(-k.as_), qg[i]);
+        OPS_P qg[i] = mul2(qg[i], splat(k.Gf));
+        OPS_P qg[i] = mul2(qg[i], splat(k.kf));
+        OPS_P qg[i] = fm::mul2_add(qg[i], rs[i], one);
+        OPS_P g[i] = fm::f2(qg[i].x + db[i].x, qg[i].y + db[i].y);
+        OPS_P {
+            sum_pair<EPL>(aI, sh, p0 + i, l, I[i]); sum_pair<EPL>(ad, sh, p0 + i, l, d[i]); sum_pair<EPL>(aq, sh, p0 + i, l, q[i]);
         }
-        (void)rb; (void)rgg; (void)t0; (void)t1; (void)t2; (void)y;
-#endif
-        // shear branch gs = ((((-as) qg) Gf) kf) (0.5 / s) ; g = (1 + gs) + gb
-        OPS_B qg[i] = (-k.as_) * qg[i];
-        OPS_B qg[i] = qg[i] * k.Gf;
-        OPS_B qg[i] = qg[i] * k.kf;
-        OPS_B qg[i] = qg[i] * rs[i];
-        OPS_B qg[i] = 1.0f + qg[i];
-        OPS_B rg.g[k0 + i] = qg[i] + db[i];
-        OPS_B {
-            const int kk = k0 + i;
-            if (kk < sh.blk) {
-                aI[kk & 3] += I[i]; ad[kk & 3] += d[i]; aq[kk & 3] += q[i];
-            } else if (kk < sh.vec) {
-                aI[0] += I[i]; ad[0] += d[i]; aq[0] += q[i];
-            } else if (kk == sh.vec && l < sh.ntail) {
-                tI = I[i]; td = d[i]; tq = q[i];
+        if (stage_I) {
+            OPS_P *reinterpret_cast<F2 *>(ls.scr + (long)(p0 + i) * ls.ls) = I[i];
+        }
+        // Adam: m, v
+        F2 vmin = splat(3.0e38f);
+        OPS_P { t0[i] = add2(g[i], neg2(rg.m[p0 + i])); t1[i] = mul2(splat(k.omb2f), g[i]); t2[i] = mul2(rg.v[p0 + i], splat(k.b2f)); }
+        OPS_P { rg.m[p0 + i] = fma2(splat(k.w1), t0[i], rg.m[p0 + i]); rg.v[p0 + i] = fma2(t1[i], g[i], t2[i]); }
+        OPS_P { vmin.x = fminf(vmin.x, rg.v[p0 + i].x); vmin.y = fminf(vmin.y, rg.v[p0 + i].y); }   // (v is never NaN here: the loss was finite)
+        if (fminf(vmin.x, vmin.y) >= fm::SQRT_F_MIN) {
+            F2 den[NB], rd[NB], num[NB];
+            // sqrt(v) / bc2_sqrt + eps
+            OPS_P y[i] = fm::rsq2_a(rg.v[p0 + i]);
+            OPS_P { t0[i] = mul2(rg.v[p0 + i], y[i]); y[i] = mul2(y[i], half); num[i] = mul2(splat(neg_step), rg.m[p0 + i]); }
+            OPS_P t1[i] = fma2(neg2(t0[i]), t0[i], rg.v[p0 + i]);
+            OPS_P t0[i] = fma2(t1[i], y[i], t0[i]);                  // sqrt(v)
+            OPS_P t1[i] = mul2(t0[i], splat(rbc));
+            OPS_P den[i] = fma2(splat(-bc2_sqrt), t1[i], t0[i]);
+            OPS_P den[i] = fma2(splat(rbc), den[i], t1[i]);
+            OPS_P den[i] = add2(den[i], splat(k.adam_epsf));
+            // I + (neg_step m) / denom, clamp
+            OPS_P rd[i] = fm::rcp2_a(den[i]);
+            OPS_P t0[i] = fma2(neg2(den[i]), rd[i], one);
+            OPS_P rd[i] = fma2(rd[i], t0[i], rd[i]);
+            OPS_P t0[i] = mul2(num[i], rd[i]);
+            OPS_P t1[i] = fma2(neg2(den[i]), t0[i], num[i]);
+            OPS_P t0[i] = fma2(rd[i], t1[i], t0[i]);
+            OPS_P t0[i] = add2(I[i], t0[i]);
+            OPS_P rg.I[p0 + i] = fm::f2(fmaxf(t0[i].x, k.clampf), fmaxf(t0[i].y, k.clampf));   // (t0 is finite: den > 0, v and m finite)
+        } else {
+            OPS_P {
+                const float dx = sqrtf(rg.v[p0 + i].x) / bc2_sqrt + k.adam_epsf, dy = sqrtf(rg.v[p0 + i].y) / bc2_sqrt + k.adam_epsf;
+                const float xx = I[i].x + (neg_step * rg.m[p0 + i].x) / dx, xy = I[i].y + (neg_step * rg.m[p0 + i].y) / dy;
+                rg.I[p0 + i] = fm::f2(xx < k.clampf ? k.clampf : xx, xy < k.clampf ? k.clampf : xy);
             }
         }
+        // flexibility sums of the next epoch
+        {
+            double Id[2 * NB], r[2 * NB], e[2 * NB];
+            if (NC > 1) {
+                OPS_S { mq[s_] = ls.mq[(long)(2 * p0 + s_) * ls.ls]; ke[s_] = slot_ke<EPL>(rg, 2 * p0 + s_); }
+            }
+            OPS_S Id[s_] = (double)((s_ & 1) ? rg.I[p0 + (s_ >> 1)].y : rg.I[p0 + (s_ >> 1)].x);
+            OPS_S r[s_] = fm::rcp64_a(Id[s_]);
+            OPS_S e[s_] = fma(-Id[s_], r[s_], 1.0);           // rcp64_n, stage by stage
+            OPS_S e[s_] = fma(e[s_], e[s_], e[s_]);
+            OPS_S r[s_] = fma(r[s_], e[s_], r[s_]);
+            OPS_S pass1_accumulate<EPL>(rg, ls, pc, 2 * p0 + s_, r[s_], ke[s_], mq[s_], !stage_I, acc);
+        }
     }
+#undef OPS_P
+#undef OPS_S
     float *st = reinterpret_cast<float *>(ls.scr + (long)SCR_STAGE * ls.ls);
     const long fs_ = 2 * ls.ls;                 // float stride between slots
-    st[0] = ((aI[0] + aI[1]) + aI[2]) + aI[3]; st[1] = tI;
-    st[fs_] = ((ad[0] + ad[1]) + ad[2]) + ad[3]; st[fs_ + 1] = td;
-    st[2 * fs_] = ((aq[0] + aq[1]) + aq[2]) + aq[3]; st[2 * fs_ + 1] = tq;
+    st[0] = sum_rows(aI); st[1] = aI.tail;
+    st[fs_] = sum_rows(ad); st[fs_ + 1] = ad.tail;
+    st[2 * fs_] = sum_rows(aq); st[2 * fs_ + 1] = aq.tail;
 }
 
 // total loss in torch's order: scalar tail first, then the eight vector lanes (every lane, redundantly)
@@ -523,100 +641,17 @@ OPS_HD float group_loss(const BeamConsts &k, int n, const LaneStore &ls, int l)
     return (s[0] + k.am * s[1]) + k.as_ * s[2];
 }
 
-// Adam step + clamp on the lane's elements (element_update_f32, second half) and, fused behind it
-// when PASS1 is set, PASS 1 of the NEXT epoch on the updated inertias (stage-major batches as above).
-// The fast square root needs v >= 2^-101; v is an EMA of g^2, so anything smaller means g vanished on
-// every epoch so far -- tested once per lane and epoch, with the generic operators as the (cold)
-// alternative.
-template <int EPL, bool PASS1, int NBX = NB>
-OPS_HD void lane_adam(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc,
-                      float neg_step, float bc2_sqrt)
-{
-    constexpr int NB = NBX;
-    bool rare = false;
-    {
-        float t0[EPL], t1[EPL];
-#define OPS_A _Pragma("unroll") for (int kk = 0; kk < EPL; ++kk)
-        OPS_A { t0[kk] = rg.g[kk] - rg.m[kk]; t1[kk] = k.omb2f * rg.g[kk]; rg.v[kk] = rg.v[kk] * k.b2f; }
-        OPS_A { rg.m[kk] = fmaf(k.w1, t0[kk], rg.m[kk]); rg.v[kk] = fmaf(t1[kk], rg.g[kk], rg.v[kk]); }
-        float vmin = rg.v[0];
-        OPS_A vmin = fminf(vmin, rg.v[kk]);                         // (v is never NaN here: the loss was finite)
-        rare = !(vmin >= fm::SQRT_F_MIN);
-#undef OPS_A
-    }
-    if (!rare) {
-        const float rbc = fm::rcp_r(bc2_sqrt);
-        SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int k0 = 0; k0 < EPL; k0 += NB) {
-            float y[NB], den[NB], rd[NB], t0[NB], t1[NB], num[NB];
-            double Id[NB], r[NB];
-#if defined(__CUDA_ARCH__)
-            // sqrt(v) / bc2_sqrt + eps
-            OPS_B y[i] = fm::rsq_a(rg.v[k0 + i]);
-            OPS_B { t0[i] = rg.v[k0 + i] * y[i]; y[i] = y[i] * 0.5f; num[i] = neg_step * rg.m[k0 + i]; }
-            OPS_B t1[i] = fmaf(-t0[i], t0[i], rg.v[k0 + i]);
-            OPS_B t0[i] = fmaf(t1[i], y[i], t0[i]);                  // sqrt(v)
-            OPS_B t1[i] = t0[i] * rbc;
-            OPS_B den[i] = fmaf(-bc2_sqrt, t1[i], t0[i]);
-            OPS_B den[i] = fmaf(rbc, den[i], t1[i]);
-            OPS_B den[i] = den[i] + k.adam_epsf;
-            // I + (neg_step m) / denom, clamp
-            OPS_B rd[i] = fm::rcp_a(den[i]);
-            OPS_B t0[i] = fmaf(-den[i], rd[i], 1.0f);
-            OPS_B rd[i] = fmaf(rd[i], t0[i], rd[i]);
-            OPS_B t0[i] = num[i] * rd[i];
-            OPS_B t1[i] = fmaf(-den[i], t0[i], num[i]);
-            OPS_B t0[i] = fmaf(rd[i], t1[i], t0[i]);
-            OPS_B t0[i] = rg.I[k0 + i] + t0[i];
-            OPS_B rg.I[k0 + i] = fmaxf(t0[i], k.clampf);           // one FMNMX (t0 is finite: den > 0, v and m finite)
-            if (PASS1) {
-                double e[NB];
-                OPS_B Id[i] = (double)rg.I[k0 + i];
-                OPS_B r[i] = fm::rcp64_a(Id[i]);
-                OPS_B e[i] = fma(-Id[i], r[i], 1.0);           // rcp64_n, stage by stage
-                OPS_B e[i] = fma(e[i], e[i], e[i]);
-                OPS_B r[i] = fma(r[i], e[i], r[i]);
-            }
-#else
-            OPS_B {
-                den[i] = sqrtf(rg.v[k0 + i]) / bc2_sqrt + k.adam_epsf;
-                const float x = rg.I[k0 + i] + (neg_step * rg.m[k0 + i]) / den[i];
-                rg.I[k0 + i] = x < k.clampf ? k.clampf : x;
-                Id[i] = (double)rg.I[k0 + i];
-                r[i] = 1.0 / Id[i];
-            }
-            (void)y; (void)rd; (void)t0; (void)t1; (void)num; (void)rbc;
-#endif
-            if (PASS1) {
-                OPS_B pass1_accumulate<EPL>(rg, ls, pc, k0 + i, r[i], a);
-            }
-        }
-    } else {
-#pragma unroll                                  // (static indices: a rolled loop would push the state arrays to local memory)
-        for (int kk = 0; kk < EPL; ++kk) {
-            const float denom = sqrtf(rg.v[kk]) / bc2_sqrt + k.adam_epsf;
-            const float x = rg.I[kk] + (neg_step * rg.m[kk]) / denom;
-            rg.I[kk] = x < k.clampf ? k.clampf : x;
-        }
-        if (PASS1) lane_pass1<EPL>(rg, ls, pc);
-    }
-}
-#undef OPS_B
-
 // ---------------------------------------------------------------------------------------------
 // once per beam: the record (SingleCore:221-249).  M, V, u, theta belong to the LAST ANALYSED
-// inertias, i.e. the ones still in rg.I when the stop decision is taken (before lane_adam).
+// inertias, i.e. the ones the beam's last pass started from (parked by it, stage_I); rg.I holds the stepped ones.
 // ---------------------------------------------------------------------------------------------
 template <int EPL>
 OPS_HD void lane_emit_forces(int n, const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe, int l,
                              bool fields, float *shear, float *moment)
 {
-    float *stage = reinterpret_cast<float *>(ls.scr);        // I of slot kk at float index (kk >> 1) * 2 ls + (kk & 1)
 #pragma unroll
     for (int kk = 0; kk < EPL; ++kk) {
         const int e = LPB * kk + l;
-        stage[(long)(kk >> 1) * 2 * ls.ls + (kk & 1)] = rg.I[kk];
         if (e < n) {
             double Mc = 0.0, Qv = 0.0;
             if (fields) element_forces<EPL>(rg, ls, gs, invLe, kk, Mc, Qv);
@@ -626,7 +661,8 @@ OPS_HD void lane_emit_forces(int n, const LaneRegs<EPL> &rg, const LaneStore &ls
     }
 }
 
-// lane 0: displacements by integrating the curvature (flex_deflections_march) from the staged inertias
+// lane 0: displacements by integrating the curvature (flex_deflections_march) from the inertias the beam's last pass
+// parked in the scratch columns (pair j of a lane = float pair at slot j)
 OPS_HD void group_emit_displacements(const BeamConsts &k, const FlexBeam &fb, const LaneStore &ls0,
                                      const GroupStore &gs, bool fields, double *defl, double *rot)
 {
@@ -661,7 +697,7 @@ OPS_HD void lane_emit_inertias(int n, const LaneRegs<EPL> &rg, int l, float *I_o
 #pragma unroll
     for (int kk = 0; kk < EPL; ++kk) {
         const int e = LPB * kk + l;
-        if (e < n) I_out[e] = rg.I[kk];
+        if (e < n) I_out[e] = (kk & 1) ? rg.I[kk >> 1].y : rg.I[kk >> 1].x;
     }
 }
 

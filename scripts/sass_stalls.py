@@ -26,10 +26,10 @@ for i, line in enumerate(open(src), 1):
     m = re.match(r"OPS_HD\s+[\w:<>\s\*&]+?\s+(\w+)\s*\(", line)
     if m:
         funcs.append((i, m.group(1)))
-# line range of the cold generic-operator branch of lane_adam
+# line range of the cold generic-operator branch of the pass (Adam's v below the fast square root's range)
 _src = open(src).read().split("\n")
-_g0 = next(i for i, t in enumerate(_src, 1) if "static indices: a rolled loop" in t)
-GENERIC = (_g0, _g0 + 8)
+_g0 = next(i for i, t in enumerate(_src, 1) if "const float dx = sqrtf(" in t)
+GENERIC = (_g0 - 1, _g0 + 4)
 
 
 def func_of(line):
@@ -66,8 +66,8 @@ while i < len(body):
         if m2:
             stall = (int(m2.group(1), 16) >> 41) & 0xF
             inner = func_of(in_line) if in_file == "beamopt_lanes.cuh" else in_file.replace(".cuh", "")
-            if inner == "lane_adam":
-                inner = "lane_adam(generic ops)" if GENERIC[0] <= in_line <= GENERIC[1] else "lane_adam"
+            if inner == "lane_pass":
+                inner = "lane_pass(generic ops)" if GENERIC[0] <= in_line <= GENERIC[1] else "lane_pass"
             key = (cur_file, cur_line, inner)
             a = agg.setdefault(key, [0, 0, 0])
             a[0] += 1; a[1] += stall; a[2] += stall >= 4

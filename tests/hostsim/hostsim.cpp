@@ -266,7 +266,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             group_table_init(gs[c]);
             bad = group_fetch(k, L[b], gs[c], fb[c]);
             for (int l = 0; l < LPB; ++l) {
-                if (!bad) { lane_init<EPL>(k, n, fb[c], gs[c], ls[c][l], l, rg[c][l]); lane_pass1<EPL>(rg[c][l], ls[c][l], pass1_consts(fb[c])); }
+                if (!bad) { lane_init<EPL>(k, n, fb[c], gs[c], ls[c][l], l, rg[c][l]); lane_pass1<EPL>(rg[c][l], ls[c][l], pass1_consts(fb[c]), false); }
                 else lane_reset<EPL>(k, rg[c][l]);
             }
         }
@@ -283,8 +283,11 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
                 if (NC > 1) for (int l = 0; l < LPB; ++l) lane_case_squares<EPL>(rg[c][l], ls[c][l], gs[c], fb[c].invLe);
             }
             float lv[NC][LPB];
+            const bool stage_I = (t + 1 >= k.max_epochs) || (k.early_stop && counter + 1 >= k.patience);
             for (int c = 0; c < NC; ++c)
-                for (int l = 0; l < LPB; ++l) lane_forces<EPL, NC>(k, n, rg[c][l], ls[c][l], gs[c], fb[c].invLe, l, c);
+                for (int l = 0; l < LPB; ++l)
+                    lane_pass<EPL, NC>(k, n, rg[c][l], ls[c][l], gs[c], pass1_consts(fb[c]), fb[c].invLe, l, c, neg_step, bc2_sqrt,
+                                       stage_I);
             for (int c = 0; c < NC; ++c)
                 for (int l = 0; l < LPB; ++l) lv[c][l] = group_loss(k, n, ls[c][l], l);
             for (int c = 0; c < NC; ++c)
@@ -298,9 +301,9 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
                 if (counter >= k.patience) done = true;
             }
             if (t >= k.max_epochs) done = true;
-            if (!done)
+            if (!done && stage_I)
                 for (int c = 0; c < NC; ++c)
-                    for (int l = 0; l < LPB; ++l) lane_adam<EPL, true>(k, rg[c][l], ls[c][l], pass1_consts(fb[c]), neg_step, bc2_sqrt);
+                    for (int l = 0; l < LPB; ++l) lane_pass1<EPL>(rg[c][l], ls[c][l], pass1_consts(fb[c]), true);
         }
         const bool fields = (t > 0) && (bad == 0);
         for (int c = 0; c < NC; ++c) {
@@ -308,10 +311,8 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             for (int l = 0; l < LPB; ++l)
                 lane_emit_forces<EPL>(n, rg[c][l], ls[c][l], gs[c], fb[c].invLe, l, fields, shear + bc * n, moment + bc * n);
             group_emit_displacements(k, fb[c], ls[c][0], gs[c], fields, defl + bc * nn, rot + bc * nn);
-            for (int l = 0; l < LPB; ++l) {
-                if (t > 0) lane_adam<EPL, false>(k, rg[c][l], ls[c][l], pass1_consts(fb[c]), neg_step, bc2_sqrt);
+            for (int l = 0; l < LPB; ++l)
                 if (c == 0) lane_emit_inertias<EPL>(n, rg[c][l], l, I_values + b * n);
-            }
         }
         epochs[b] = t; loss[b] = lossf; status[b] = bad;
     }

@@ -214,18 +214,18 @@ def test_peer_copy_of_a_record_moves_exactly_its_rows(num_nodes, num_cases):
 
 
 def test_batch_size_of_the_stage_major_batches_does_not_change_the_bits(tmp_path):
-    """The kernel instances differ in the number of slots per stage-major batch (five; six in the 320-thread
-    scatter instance): a pure reordering of independent per-element chains.  The same source built with six and with
-    four slots per batch produces the bits of the default build (single case and four load cases)."""
+    """The number of slot pairs per stage-major batch of the pass (three by default; a build knob,
+    OPS_LANES_NBP) is a pure reordering of independent per-element chains: the same source built with two pairs per
+    batch produces the bits of the default build (single case and four load cases)."""
     import ctypes as C
     import subprocess
     from tests import helpers
     base = helpers.hostsim_lib()
     libs = {}
-    for nb in (4, 6):
+    for nb in (2,):
         path = str(tmp_path / f"libhostsim_nb{nb}.so")
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                        f"-DOPS_LANES_NB={nb}", "-o", path, helpers._HS_SRC], check=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                        f"-DOPS_LANES_NBP={nb}", "-o", path, helpers._HS_SRC], check=True)
         libs[nb] = C.CDLL(path)
     for num_cases, beams in ((1, 24), (4, 8)):
         p = BeamOptParams.for_script("MC").replace(num_cases=num_cases, max_e=150)
