@@ -73,8 +73,13 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
 // 10 % more fixed-latency `wait` stalls (profiles/r01_v6_ab_scatter.txt, r01_v6_scatter_instance_ncu.md).
 // TFIX: compile-time CTA size (0 = blockDim.x).  With it every shared-memory column stride is an immediate
 // and the [slot][thread] addressing costs no integer instructions.
+#ifdef OPS_LANES_MAXNREG
+#define OPS_LANES_BOUNDS __maxnreg__(OPS_LANES_MAXNREG)      /* A/B knob: register cap instead of the thread bound */
+#else
+#define OPS_LANES_BOUNDS __launch_bounds__(TFIX ? TFIX : LANES_MAX_THREADS, 1)
+#endif
 template <int EPL, int NFIX, int NC, int TFIX, bool SC>
-__global__ void __launch_bounds__(TFIX ? TFIX : LANES_MAX_THREADS, 1)
+__global__ void OPS_LANES_BOUNDS
 beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -116,6 +121,15 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     __shared__ unsigned int cta_next;
     if (tid == 0) cta_next = 0;
     __syncthreads();
+#ifdef OPS_LANES_STAGGER_NS
+    // A/B knob: warps start their first epoch OPS_LANES_STAGGER_NS apart (per scheduler slot w / 4, plus a quarter of
+    // that per scheduler), so that the resident warps are not all in the same phase of the epoch at the same time
+    {
+        const unsigned w = tid >> 5;
+        unsigned ns = (w >> 2) * OPS_LANES_STAGGER_NS + (w & 3) * (OPS_LANES_STAGGER_NS / 4);
+        while (ns > 0) { const unsigned step = ns > 1000000u ? 1000000u : ns; __nanosleep(step); ns -= step; }
+    }
+#endif
 
     LaneRegs<EPL> rg;
     FlexBeam fb;
