@@ -251,6 +251,65 @@ int ops_pipe_probe(int op, int iters, double *warp_inst_per_clk_per_sm, void *cu
 int ops_fastmath_selftest(int64_t samples, int64_t *mismatches3, int64_t *samples_run, double *rcp64_max_rel_err,
                           void *cuda_stream);
 
+/*
+ * ---------------------------------------------------------------------------------------------------------------------
+ * Frame optimiser: the optimisation loop of OpenPyStruct_FrameOpt_Discrete_Beta.py:179-206 for a
+ * batch of rectangular frames, one CTA per frame.  Per epoch it replaces setup_frame_model (:75-139) + ops.analyze(1)
+ * (:183) + compute_combined_loss (:141-160) + backward / Adam / clamp (:184-189) + the early-stop test (:194-205).
+ * Constants: the script's module-level block (:14-44) plus the literals of the loss and torch's Adam defaults.
+ */
+typedef struct OpsFrameOptParams {
+    int32_t struct_size;     /* sizeof(OpsFrameOptParams) -- ABI guard */
+    int32_t max_bays;        /* max_bays (10): upper bound of num_bays[] in a launch, sizes the shared memory (<= 16) */
+    int32_t max_stories;     /* max_stories (10) */
+    int32_t max_epochs;      /* num_epochs (5000) */
+    int32_t patience;        /* 10 */
+    int32_t early_stop;      /* 1 = reference behaviour; 0 = run exactly max_epochs */
+    double E;                /* 200e9 */
+    double G;                /* E / (2 (1 + nu)) */
+    double A;                /* 0.02: cross-section area of every member */
+    double I0;               /* 5e-4 */
+    double alpha_moment;     /* 1e-2 */
+    double alpha_shear;      /* 1e-2 */
+    double shear_k;          /* 0.03: A_local = k * sqrt(I) (:156) */
+    double bending_eps;      /* 1e-8: 2 E I + 1e-8 (:155) */
+    double lateral_load;     /* 1e4: nodal load in x on the left-hand nodes above ground (:129-131) */
+    double vertical_load;    /* -1e4: eleLoad -beamUniform w w on every beam (:135-138) */
+    double lr;               /* 0.005, constant (no scheduler) */
+    double tolerance;        /* 1e-3 */
+    double bay_width;        /* 6.0 */
+    double story_height;     /* 3.0 */
+    double clamp_min;        /* 1e-8 (:188-189) */
+    double beta1, beta2, adam_eps;   /* torch.optim.Adam defaults */
+} OpsFrameOptParams;
+
+/* columns + beams of the largest frame a launch admits = row width of I_values / moment / shear */
+int ops_frameopt_max_elements(const OpsFrameOptParams *p);
+
+/* host_table receives 2*max_epochs floats [-(lr/bc1_t), sqrt(bc2_t)], t = 1..max_epochs (see ops_beamopt_fill_schedule) */
+int ops_frameopt_fill_schedule(const OpsFrameOptParams *p, float *host_table);
+
+/*
+ * Device pointers, stream-ordered, caller-owned buffers (conventions of ops_beamopt_launch).  Members are numbered like
+ * the reference: columns story by story (:104-111), then the beams of every elevated story (:114-121).
+ *   num_bays, num_stories  i32[B]                  the frame (the script draws both with random.randint, :50-51)
+ *   d_schedule             f32[2*max_epochs]
+ *   I_values               f32[B][max_elements]    opt_I: inertias after the last Adam step + clamp (unused tail 0)
+ *   loss_history           f32[B][max_epochs]      total_loss.item() per epoch (:191-192), NaN beyond `epochs`
+ *   moment, shear          f64[B][max_elements]    eleResponse(e,'forces')[2|1] of the LAST analysed inertias
+ *   best_loss              f64[B]                  best_loss of the stop test (:194-196)
+ *   epochs                 i32[B]                  iterations executed
+ *   status                 i32[B]                  0 ok, 1 non-SPD pivot / non-finite loss, 2 frame outside max_bays / max_stories
+ */
+int ops_frameopt_launch(const OpsFrameOptParams *p, int64_t B, const int32_t *num_bays, const int32_t *num_stories,
+                        const float *d_schedule, float *I_values, float *loss_history, double *moment, double *shear,
+                        double *best_loss, int32_t *epochs, int32_t *status, void *cuda_stream);
+
+/* host-buffer convenience around ops_frameopt_launch (allocates, copies, runs, copies back, frees) */
+int ops_frameopt_run_host(const OpsFrameOptParams *p, int64_t B, const int32_t *num_bays, const int32_t *num_stories,
+                          float *I_values, float *loss_history, double *moment, double *shear, double *best_loss,
+                          int32_t *epochs, int32_t *status, int device, float *elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ EXPORTS = (
     "ops_beamopt_session_create", "ops_beamopt_session_arrays", "ops_beamopt_session_run",
     "ops_beamopt_session_destroy",
     "ops_beamopt_launch_scatter", "ops_peer_alloc", "ops_peer_open", "ops_peer_close", "ops_peer_free",
+    "ops_frameopt_max_elements", "ops_frameopt_fill_schedule", "ops_frameopt_launch", "ops_frameopt_run_host",
 )
 
 
@@ -32,6 +33,18 @@ class OpsBeamOptParams(C.Structure):
         ("lr", C.c_double), ("gamma", C.c_double), ("alpha_moment", C.c_double),
         ("alpha_shear", C.c_double), ("tolerance", C.c_double), ("shear_k", C.c_double),
         ("bending_eps", C.c_double), ("clamp_min", C.c_double), ("beta1", C.c_double),
+        ("beta2", C.c_double), ("adam_eps", C.c_double),
+    ]
+
+
+class OpsFrameOptParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("max_bays", C.c_int32), ("max_stories", C.c_int32), ("max_epochs", C.c_int32),
+        ("patience", C.c_int32), ("early_stop", C.c_int32),
+        ("E", C.c_double), ("G", C.c_double), ("A", C.c_double), ("I0", C.c_double), ("alpha_moment", C.c_double),
+        ("alpha_shear", C.c_double), ("shear_k", C.c_double), ("bending_eps", C.c_double),
+        ("lateral_load", C.c_double), ("vertical_load", C.c_double), ("lr", C.c_double), ("tolerance", C.c_double),
+        ("bay_width", C.c_double), ("story_height", C.c_double), ("clamp_min", C.c_double), ("beta1", C.c_double),
         ("beta2", C.c_double), ("adam_eps", C.c_double),
     ]
 
@@ -97,6 +110,11 @@ def lib():
         L.ops_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ops_peer_close.argtypes = [C.c_void_p]
         L.ops_peer_free.argtypes = [C.c_void_p]
+        L.ops_frameopt_max_elements.argtypes = [C.POINTER(OpsFrameOptParams)]
+        L.ops_frameopt_fill_schedule.argtypes = [C.POINTER(OpsFrameOptParams), C.c_void_p]
+        L.ops_frameopt_launch.argtypes = [C.POINTER(OpsFrameOptParams), C.c_int64] + [C.c_void_p] * 11
+        L.ops_frameopt_run_host.argtypes = [C.POINTER(OpsFrameOptParams), C.c_int64] + [C.c_void_p] * 9 + \
+            [C.c_int, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
