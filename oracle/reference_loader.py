@@ -206,3 +206,63 @@ def run_reference_frame(seed: int, overrides=None):
             else:
                 sys.modules[k] = v
     return ns, tr
+
+
+# ------------------------------------------------------------------------------------------------
+# Trainer data block (SURVEY 8f row 3 and the loader of 3.4): OpenPyStruct_PINN_MultiCase.py from its first line up to
+# "# Convert to PyTorch Tensors" (:1-369) -- hyper-parameters, pad_sequences / unify_label_with_c / fit_transform_3d /
+# merge_sub_features, json.load of "StructDataLite.json", padding, grouping by n_cases, the permutation split, the
+# StandardScalers and the label aggregation -- executed verbatim in a directory that holds a dataset written by the
+# product (dataset.save_json) under the file name the trainer opens.
+# ------------------------------------------------------------------------------------------------
+TRAINER_SCRIPT = "OpenPyStruct_PINN_MultiCase.py"
+
+
+def trainer_reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_DIR, TRAINER_SCRIPT))
+
+
+def run_reference_trainer_block(dataset_json: str, seed: int, overrides=None) -> dict:
+    """np.random.seed(seed) (the script relies on the global numpy state for its split, :260); the trainer's own source
+    up to the tensors.  ``overrides``: text-level replacements of its constants, e.g. {"n_cases = 6": "n_cases = 4"}.
+    Returns its namespace (X_train_flat, X_val_flat, Y_train_std, Y_val_std, train_idx, val_idx, scalers_*, ...)."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    import numpy as np
+    saved = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.lines",
+                                             "matplotlib.patches", "seaborn")}
+    mpl = types.ModuleType("matplotlib")
+    mpl.__path__ = []
+    for sub in ("pyplot", "cm", "lines", "patches"):
+        m = _Anything()
+        setattr(mpl, sub, m)
+        sys.modules["matplotlib." + sub] = m
+    sys.modules["matplotlib"] = mpl
+    sys.modules["seaborn"] = _Anything()
+    path = os.path.join(REFERENCE_DIR, TRAINER_SCRIPT)
+    with open(path, "r") as fh:
+        text = fh.read()
+    text = text[:text.index("# Convert to PyTorch Tensors")]
+    for old, new in (overrides or {}).items():
+        if old not in text:
+            raise KeyError(old)
+        text = text.replace(old, new)
+    ns = {"__name__": "_reference_trainer", "__file__": path}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        shutil.copyfile(dataset_json, os.path.join(td, "StructDataLite.json"))
+        os.chdir(td)
+        try:
+            np.random.seed(seed)
+            with contextlib.redirect_stdout(io.StringIO()):
+                exec(compile(text, path, "exec"), ns)
+        finally:
+            os.chdir(cwd)
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+    return ns

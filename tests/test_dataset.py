@@ -98,3 +98,52 @@ def test_trainer_preprocess_matches_the_reference_block():
             assert np.allclose(g[:, cols], w[:, cols], rtol=1e-4, atol=1e-4), key
         assert ok.mean() > 0.9
     assert isinstance(got["X_train"], torch.Tensor)
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference trainer's OWN data block (OpenPyStruct_PINN_MultiCase.py:1-369 executed verbatim on a dataset the
+# product's writer emitted; frozen by tests/golden/make_trainer_golden.py) against dataset.trainer_preprocess
+# --------------------------------------------------------------------------------------------------
+import os          # noqa: E402
+import pytest      # noqa: E402
+
+_TG = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trainer_goldens.npz"))
+
+
+def _trainer_golden_case(i):
+    col = {k[4:]: _TG[k] for k in _TG.files if k.startswith("col:")}
+    n_cases, c, seed, split = _TG[f"{i}:config"]
+    ref = {k.split(":", 1)[1]: _TG[k] for k in _TG.files if k.startswith(f"{i}:")}
+    return dataset.to_training_data(col), int(n_cases), float(c), int(seed), float(split), ref
+
+
+def _check_trainer_block(device):
+    for i in (0, 1):
+        data, n_cases, c, seed, split, ref = _trainer_golden_case(i)
+        got = dataset.trainer_preprocess(data, n_cases, c=c, train_split=split, seed=seed, device=device)
+        assert got["X_train"].device.type == device
+        # the loader half: json.load -> pad -> trim -> reshape by n_cases (PINN:190-258) and the permutation split (:260-264)
+        assert np.array_equal(got["train_idx"].cpu().numpy(), ref["train_idx"])
+        assert np.array_equal(got["val_idx"].cpu().numpy(), ref["val_idx"])
+        # labels whose training column is constant up to fp32 rounding are standardised by a ~1e-7 scale: the
+        # reference's own numbers are rounding noise there (sklearn divides by that scale); compared where the scale is real
+        Yt = ref["Y_train_std"]
+        I_g = ref["I_grouped"][ref["train_idx"]]
+        lab = np.concatenate([I_g.mean(axis=1) + c * I_g.std(axis=1)], axis=1)
+        real = np.ones(Yt.shape[1], bool)
+        real[:lab.shape[1]] = lab.std(axis=0) > 1e-4 * (np.abs(lab).mean(axis=0) + 1e-30)
+        for key, want, cols in (("X_train", ref["X_train_flat"], slice(None)), ("X_val", ref["X_val_flat"], slice(None)),
+                                ("Y_train", Yt, real), ("Y_val", ref["Y_val_std"], real)):
+            g = got[key].cpu().numpy()
+            assert g.shape == want.shape and np.isfinite(g).all(), key
+            assert np.allclose(g[:, cols], want[:, cols], rtol=2e-4, atol=2e-4), (i, key, np.abs(g[:, cols] - want[:, cols]).max())
+        assert real.mean() > 0.9
+
+
+def test_trainer_block_equals_the_reference_trainers_own_code_cpu():
+    _check_trainer_block("cpu")
+
+
+@pytest.mark.gpu
+def test_trainer_block_equals_the_reference_trainers_own_code_on_the_device():
+    _check_trainer_block("cuda")
