@@ -154,6 +154,10 @@ int ops_beamopt_launch_scatter(const OpsBeamOptParams *p, int64_t B,
                                int n_dest, const OpsBeamOptRecordArrays *dests, int64_t row0,
                                void *d_workspace, size_t workspace_bytes, void *cuda_stream);
 
+/* 1 when ops_beamopt_launch_scatter serves this parameter block (production lanes kernel: default solver, num_nodes <= 169,
+ * multi-case only at <= 105 nodes), else 0.  Depends on `p` alone: every rank of a job decides alike before any collective. */
+int ops_beamopt_scatter_supported(const OpsBeamOptParams *p);
+
 /*
  * Peer-visible device buffers for the scatter above (CUDA IPC; one process per GPU).  ops_peer_alloc: cudaMalloc on
  * the current device + a 64-byte handle to send to the other ranks; ops_peer_open: map a peer's buffer into this
@@ -250,6 +254,33 @@ int ops_pipe_probe(int op, int iters, double *warp_inst_per_clk_per_sm, void *cu
  */
 int ops_fastmath_selftest(int64_t samples, int64_t *mismatches3, int64_t *samples_run, double *rcp64_max_rel_err,
                           void *cuda_stream);
+
+/*
+ * Host side of the seam: the reference's support / load sampling (SingleCore:133-160; it "stays on the host, unchanged",
+ * SURVEY 8a row 3) drawn natively from a bit-exact replica of CPython's `random` -- the same stream random.seed(seed)
+ * gives the reference's own statements -- straight into the arrays of ops_beamopt_launch.  No device involved.
+ *   ops_sampler_create      random.Random(seed), 0 <= seed < 2^64
+ *   ops_sampler_random / ops_sampler_randint   one random.random() / random.randint(a, b) of the stream (tests, frames)
+ *   ops_sampler_draw_cases  `count` consecutive generate_sample() draws (count = beams * num_cases; consecutive cases
+ *                           share a beam and the supports / length of its first case).  flag = 0: the fixed
+ *                           roller_nodes / available_nodes lists (1-based tags, SingleCore:58-66); flag = 1: per sample
+ *                           L = L_min + uniform(0, L_max) and 1..N_rollers_max rollers by choice + remove (:133-151).
+ *                           Then always k = randint(1, M_forces_max), sample(available, k), k x uniform(min_force, max_force).
+ *     fixed_uy u8[beams][num_nodes], force_nodes i32[count][max_forces] (0-based, -1 unused), force_vals f64[count][max_forces],
+ *     L_out f64[beams]: the ABI arrays;  roller_tags i32[count][roller_width], force_tags i32[count][max_forces] (1-based tags,
+ *     0 unused) and case_L f64[count]: what the record needs besides (roller_nodes, force_nodes, L of the 13-key dict).
+ */
+typedef struct OpsSampler OpsSampler;
+int ops_sampler_create(uint64_t seed, OpsSampler **out);
+void ops_sampler_destroy(OpsSampler *s);
+double ops_sampler_random(OpsSampler *s);
+int ops_sampler_randint(OpsSampler *s, int a, int b);
+int ops_sampler_draw_cases(OpsSampler *s, int64_t count, int32_t num_nodes, int32_t flag, double L,
+                           const int32_t *roller_nodes, int32_t n_rollers, const int32_t *available_nodes,
+                           int32_t n_available, double L_max, double L_min, int32_t N_rollers_max, int32_t M_forces_max,
+                           double max_force, double min_force, int32_t num_cases, int32_t max_forces,
+                           uint8_t *fixed_uy, int32_t *force_nodes, double *force_vals, double *L_out,
+                           int32_t *roller_tags, int32_t roller_width, int32_t *force_tags, double *case_L);
 
 /*
  * ---------------------------------------------------------------------------------------------------------------------

@@ -18,7 +18,8 @@ EXPORTS = (
     "ops_fp64_peak_probe", "ops_fastmath_selftest", "ops_pipe_probe",
     "ops_beamopt_session_create", "ops_beamopt_session_arrays", "ops_beamopt_session_run",
     "ops_beamopt_session_destroy",
-    "ops_beamopt_launch_scatter", "ops_peer_alloc", "ops_peer_open", "ops_peer_close", "ops_peer_free",
+    "ops_beamopt_launch_scatter", "ops_beamopt_scatter_supported", "ops_peer_alloc", "ops_peer_open", "ops_peer_close", "ops_peer_free",
+    "ops_sampler_create", "ops_sampler_destroy", "ops_sampler_random", "ops_sampler_randint", "ops_sampler_draw_cases",
     "ops_frameopt_max_elements", "ops_frameopt_fill_schedule", "ops_frameopt_launch", "ops_frameopt_run_host",
 )
 
@@ -106,10 +107,21 @@ def lib():
         L.ops_beamopt_session_destroy.restype = None
         L.ops_beamopt_launch_scatter.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.POINTER(OpsBeamOptRecordArrays), C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ops_beamopt_scatter_supported.argtypes = [C.POINTER(OpsBeamOptParams)]
         L.ops_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
         L.ops_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ops_peer_close.argtypes = [C.c_void_p]
         L.ops_peer_free.argtypes = [C.c_void_p]
+        L.ops_sampler_create.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+        L.ops_sampler_destroy.argtypes = [C.c_void_p]
+        L.ops_sampler_destroy.restype = None
+        L.ops_sampler_random.argtypes = [C.c_void_p]
+        L.ops_sampler_random.restype = C.c_double
+        L.ops_sampler_randint.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ops_sampler_draw_cases.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32,
+                                             C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32,
+                                             C.c_double, C.c_double, C.c_int32, C.c_int32] + [C.c_void_p] * 5 + \
+            [C.c_int32, C.c_void_p, C.c_void_p]
         L.ops_frameopt_max_elements.argtypes = [C.POINTER(OpsFrameOptParams)]
         L.ops_frameopt_fill_schedule.argtypes = [C.POINTER(OpsFrameOptParams), C.c_void_p]
         L.ops_frameopt_launch.argtypes = [C.POINTER(OpsFrameOptParams), C.c_int64] + [C.c_void_p] * 11

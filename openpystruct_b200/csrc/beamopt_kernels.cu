@@ -710,6 +710,17 @@ int ops_beamopt_launch_scatter(const OpsBeamOptParams *p, int64_t B,
                        nullptr, nullptr, nullptr, nullptr, n_dest, dests, row0, d_workspace, workspace_bytes, cuda_stream);
 }
 
+// Whether ops_beamopt_launch_scatter serves this configuration (a function of the parameter block alone, so every rank
+// of a job gets the same answer without talking to the others -- ranks with an empty shard included).
+int ops_beamopt_scatter_supported(const OpsBeamOptParams *p)
+{
+    BeamConsts k;
+    if (make_consts(p, &k)) return 0;
+    LaunchPlan pl;
+    if (plan_launch(k, p->num_cases, 1, p->solver, &pl)) return 0;
+    return (pl.lanes && lanes_scatter_supported(pl.lp)) ? 1 : 0;
+}
+
 // --- peer-visible device buffers (CUDA IPC): the dataset arrays the in-kernel scatter writes over NVLink ---
 int ops_peer_alloc(size_t bytes, void **dptr, unsigned char *handle64)
 {

@@ -28,16 +28,28 @@ _DENSE = ("I_values", "shear_forces", "bending_moments", "node_positions", "rota
 _SCALAR = ("num_nodes", "L")
 
 
-def columnar_from_run(params: BeamOptParams, cases: Sequence, out: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+def columnar_from_run(params: BeamOptParams, cases, out: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     """Kernel outputs + the sampled cases -> one array per key of the reference record (failed beams
-    dropped, MultiCore:265).  Ragged keys are (values, lengths) pairs padded with NaN / -1."""
+    dropped, MultiCore:265).  Ragged keys are (values, lengths) pairs padded with NaN / -1.
+    ``cases``: the list of ``sampling.sample_case`` tuples, or a ``sampling.PackedCases`` (native sampler), which is
+    consumed as arrays -- no per-record Python objects."""
+    from .sampling import PackedCases
     C = params.num_cases
+    packed = isinstance(cases, PackedCases)
     B = len(cases) // C
     keep_b = np.flatnonzero(np.asarray(out["status"][:B]) == 0)
     rec = (keep_b[:, None] * C + np.arange(C)[None, :]).reshape(-1)          # record index = beam * C + case
     nn = params.num_nodes
-    L = np.array([cases[b * C][0] for b in keep_b], np.float64)
-    node_positions = np.stack([np.linspace(0, l_, nn) for l_ in L]) if len(L) else np.zeros((0, nn))
+    if packed:
+        L = np.asarray(cases.L, np.float64)[keep_b]
+        node_positions = np.linspace(0.0, 1.0, nn)[None, :] * L[:, None] if len(L) else np.zeros((0, nn))
+        if len(L):                                                           # np.linspace(0, L, nn) bit for bit
+            step = L / (nn - 1)
+            node_positions = np.arange(nn)[None, :] * step[:, None]
+            node_positions[:, -1] = L
+    else:
+        L = np.array([cases[b * C][0] for b in keep_b], np.float64)
+        node_positions = np.stack([np.linspace(0, l_, nn) for l_ in L]) if len(L) else np.zeros((0, nn))
 
     def ragged(get, dtype, pad):
         rows = [get(i) for i in rec]
@@ -49,8 +61,15 @@ def columnar_from_run(params: BeamOptParams, cases: Sequence, out: Dict[str, np.
             lens[i] = len(r)
         return vals, lens
 
+    def ragged_packed(tags, values, dtype, pad):
+        """tags: i32 [records, width0] 1-based, 0 = unused (used slots first); values: same shape or None."""
+        lens = np.count_nonzero(tags, axis=1).astype(np.int32)
+        width = int(lens.max()) if len(lens) else 0
+        src = tags if values is None else values
+        vals = np.where(np.arange(width)[None, :] < lens[:, None], src[:, :width], pad).astype(dtype)
+        return vals, lens
+
     per_rec_np = np.repeat(node_positions, C, axis=0)
-    rollers = lambda i: cases[(i // C) * C][1]                               # noqa: E731  (supports shared by the cases)
     col = {
         "I_values": np.repeat(np.asarray(out["I"])[keep_b], C, axis=0),
         "shear_forces": np.asarray(out["shear"])[keep_b].reshape(len(rec), -1),
@@ -61,9 +80,18 @@ def columnar_from_run(params: BeamOptParams, cases: Sequence, out: Dict[str, np.
         "num_nodes": np.full(len(rec), nn, np.int32),
         "L": np.repeat(L, C),
     }
-    col["roller_nodes"], col["roller_nodes_len"] = ragged(rollers, np.int32, -1)
-    col["force_nodes"], col["force_nodes_len"] = ragged(lambda i: cases[i][2], np.int32, -1)
-    col["force_values"], col["force_values_len"] = ragged(lambda i: cases[i][3], np.float64, np.nan)
+    if packed:
+        first = (rec // C) * C                                               # supports shared by the cases of a beam
+        col["roller_nodes"], col["roller_nodes_len"] = ragged_packed(cases.roller_tags[first], None, np.int32, -1)
+        ft = cases.force_tags[rec]
+        col["force_nodes"], col["force_nodes_len"] = ragged_packed(ft, None, np.int32, -1)
+        fv = cases.force_vals.reshape(len(cases), -1)[rec]
+        col["force_values"], col["force_values_len"] = ragged_packed(ft, fv, np.float64, np.nan)
+    else:
+        rollers = lambda i: cases[(i // C) * C][1]                           # noqa: E731  (supports shared by the cases)
+        col["roller_nodes"], col["roller_nodes_len"] = ragged(rollers, np.int32, -1)
+        col["force_nodes"], col["force_nodes_len"] = ragged(lambda i: cases[i][2], np.int32, -1)
+        col["force_values"], col["force_values_len"] = ragged(lambda i: cases[i][3], np.float64, np.nan)
     rx = np.where(col["roller_nodes"] >= 0, np.take_along_axis(
         per_rec_np, np.clip(col["roller_nodes"] - 1, 0, nn - 1), axis=1), np.nan) if len(rec) else \
         np.zeros((0, 0))

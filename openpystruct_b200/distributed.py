@@ -140,6 +140,12 @@ class PeerDataset:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 8:
             raise ValueError("PeerDataset: at most 8 ranks (one NVLink box)")
+        # Decided from the parameter block alone, BEFORE any collective: every rank (also one whose shard will be
+        # empty) raises alike for a configuration whose kernel has no scatter instance, and the caller's fall-back to
+        # the NCCL gather is taken by all of them.
+        if not _cabi.lib().ops_beamopt_scatter_supported(C.byref(_cabi.to_c_params(params))):
+            raise PeerUnavailable("this configuration runs a kernel without the in-kernel dataset gather "
+                                  "(solver, num_nodes > 169 or multi-case beyond 105 nodes)")
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         nn, Cc = params.num_nodes, params.num_cases
         n, Bt = nn - 1, self.num_beams
@@ -202,6 +208,7 @@ class PeerDataset:
             for f, (_, o, _, _) in zip(fields, self._layout):
                 setattr(self._dests[i], f, b + o)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ok = torch.ones(1, dtype=torch.int32, device=self.device)     # closing collective: MIN over the ranks' launch status
         self._tensors = {name: self._wrap(self._own + o, shape, dtype) for name, o, shape, dtype in self._layout}
 
     def _wrap(self, ptr: int, shape, dtype) -> torch.Tensor:
@@ -218,9 +225,12 @@ class PeerDataset:
     def tensors(self) -> Dict[str, torch.Tensor]:
         return dict(self._tensors)
 
-    def optimise(self, shard: Dict[str, torch.Tensor], row0: int) -> Dict[str, torch.Tensor]:
+    def optimise(self, shard: Dict[str, torch.Tensor], row0: int, check: bool = True) -> Dict[str, torch.Tensor]:
         """Optimise this rank's beams (``shard``: fixed_uy, force_nodes, force_vals, L on this device) into rows
-        ``row0 ...`` of every rank's dataset, then the stream barrier."""
+        ``row0 ...`` of every rank's dataset, then the stream barrier.  The closing collective carries every rank's launch
+        status (MIN): a rank whose launch failed still takes part in it and ALL ranks raise (``check=True`` reads it
+        back, one host synchronisation; a caller that pipelines steps passes ``check=False`` and calls ``check()``
+        itself)."""
         from . import ops as _ops
         C, _cabi, p = self._C, self._cabi, self.params
         B = int(shard["L"].shape[0])
@@ -231,6 +241,7 @@ class PeerDataset:
         sched = _ops.device_schedule(p, self.device)
         _ops._check_cuda(shard["fixed_uy"], shard["force_nodes"], shard["force_vals"], shard["L"], sched)
         lib = _cabi.lib()
+        rc = 0
         with torch.cuda.device(self.device):
             # no rank may still be inside the kernels of its previous call when rows are rewritten
             dist.all_reduce(self._flag, group=self.group)
@@ -242,10 +253,19 @@ class PeerDataset:
                     C.byref(cp), B, shard["fixed_uy"].data_ptr(), shard["force_nodes"].data_ptr(),
                     shard["force_vals"].data_ptr(), shard["L"].data_ptr(), sched.data_ptr(),
                     self.world, self._dests, int(row0), ws.data_ptr(), ws.numel(), stream.cuda_stream)
-                _cabi.check(rc, "ops_beamopt_launch_scatter")
                 ws.record_stream(stream)
-            dist.all_reduce(self._flag, group=self.group)      # every rank's kernel, hence every record, has landed
+            self._ok.fill_(1 if rc == 0 else 0)
+            self._rc = rc
+            dist.all_reduce(self._ok, op=dist.ReduceOp.MIN, group=self.group)   # every rank's kernel, hence every record, has landed
+        if check:
+            self.check()
         return self.tensors()
+
+    def check(self):
+        """Raises on EVERY rank when any rank's last launch failed (reads the closing collective back: host sync)."""
+        if int(self._ok.item()) == 0:
+            self._cabi.check(getattr(self, "_rc", 0), "ops_beamopt_launch_scatter")
+            raise self._cabi.CudaLibraryError("ops_beamopt_launch_scatter failed on another rank of the job")
 
     def __enter__(self):
         return self

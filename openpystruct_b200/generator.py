@@ -84,35 +84,89 @@ def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device
     into the kernel's record write where the GPUs can map each other's memory, the NCCL gather otherwise
     (``distributed.py``).  Every rank gets the whole dataset back, bit-identical to the single-GPU run."""
     dev = _require_cuda(device)
-    fixed, fn, fv, L = sampling.pack_cases(params.num_nodes, params.max_forces, cases, params.num_cases)
+    if isinstance(cases, sampling.PackedCases):
+        fixed, fn, fv, L = cases.abi_arrays()
+    else:
+        fixed, fn, fv, L = sampling.pack_cases(params.num_nodes, params.max_forces, cases, params.num_cases)
     t = lambda a: torch.from_numpy(a).pin_memory().to(dev, non_blocking=True)   # noqa: E731
     import torch.distributed as dist
     if distributed is None:
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     if distributed:
         from . import distributed as _dist
+        _require_identical_cases(fixed, fn, fv, L, dev)
         inputs = {"fixed_uy": t(fixed), "force_nodes": t(fn), "force_vals": t(fv), "L": t(L)}
         host = None
         try:
             ds = _dist.PeerDataset(params, int(L.shape[0]), device=dev)
-        except _dist.PeerUnavailable:                          # raised on every rank alike
+        except _dist.PeerUnavailable:                          # raised on every rank alike, before or inside the set-up
             ds = None
         if ds is not None:
             try:
                 start, stop, _per = _dist.shard_bounds(int(L.shape[0]), dist.get_rank(), dist.get_world_size())
                 out = ds.optimise({k: v[start:stop].contiguous() for k, v in inputs.items()}, start)
                 host = {k: v.cpu() for k, v in out.items()}      # (copies: the tensors alias the peer buffer)
-            except CudaLibraryError as ex:                     # a configuration whose kernel has no scatter instance
-                if "OPS_E_UNSUPP" not in str(ex):
-                    raise
             finally:
                 ds.close()
         if host is None:
             host = {k: v.cpu() for k, v in _dist.optimise_beams_sharded(params, inputs).items()}
-        return {k: v.numpy() for k, v in host.items()}
-    out = _ops.optimise_beams(params, t(fixed), t(fn), t(fv), t(L))
-    host = {k: v.cpu() for k, v in out.items()}
-    return {k: v.numpy() for k, v in host.items()}
+        out = {k: v.numpy() for k, v in host.items()}
+    else:
+        out = _session_run(params, fixed, fn, fv, L, dev)
+    return _rerun_unsupported(params, out, fixed, fn, fv, L, dev)
+
+
+_sessions = {}
+
+
+def _session_run(params: BeamOptParams, fixed, fn, fv, L, dev) -> dict:
+    """Single-GPU path through the host-buffer SESSION of the C ABI (pinned staging buffers, the record of each chunk
+    copied back under the next chunk's iterations): one cached session per (parameters, device), grown on demand."""
+    from . import _cabi
+    B = int(L.shape[0])
+    key = (params, dev.index)
+    sess = _sessions.get(key)
+    if sess is None or sess.max_beams < B:
+        if sess is not None:
+            sess.close()
+        if len(_sessions) >= 4:                                      # a few live parameter sets at most
+            _sessions.pop(next(iter(_sessions))).close()
+        sess = _sessions[key] = _cabi.Session(params, max(B, 1024), device=dev.index)
+    sess.load(fixed, fn, fv, L)
+    return {k: np.array(v, copy=True) for k, v in sess.run(B).items()}
+
+
+def _require_identical_cases(fixed, fn, fv, L, dev) -> None:
+    """Under torchrun every rank samples the cases itself and only optimises its block of them; the records pair the
+    gathered results with the LOCAL cases, so ranks that drew different cases (an unseeded ``random`` per process)
+    would silently corrupt the dataset.  One 16-byte all_reduce of a digest of the packed inputs makes that an error."""
+    import hashlib
+    import torch.distributed as dist
+    h = hashlib.blake2b(digest_size=8)
+    for a in (fixed, fn, fv, L):
+        h.update(np.ascontiguousarray(a).tobytes())
+    v = int.from_bytes(h.digest(), "little") >> 1                    # 63 bits: fits int64
+    lo_hi = torch.tensor([v, -v], dtype=torch.int64, device=dev)
+    dist.all_reduce(lo_hi, op=dist.ReduceOp.MAX)                     # max(v) and max(-v) = -min(v)
+    if int(lo_hi[0].item()) != v or int(lo_hi[1].item()) != -v:
+        raise RuntimeError("openpystruct_b200: the ranks of this job sampled different cases -- under torchrun pass "
+                           "the same `seed` (or an identically seeded `rng`) on every rank")
+
+
+def _rerun_unsupported(params: BeamOptParams, out: dict, fixed, fn, fv, L, dev) -> dict:
+    """Beams the three-moment kernels cannot take (status 3: more than 5 rollers -- the reference's ``ops.fix`` loop,
+    SingleCore:101-102, takes any number) are re-run with the banded LDL^T solver behind the same ABI, on this GPU
+    (under torchrun every rank does so for the few beams concerned: same inputs, same bits)."""
+    from ._cabi import to_c_params  # noqa: F401  (solver constants live in the header)
+    todo = np.flatnonzero(out["status"] == 3)
+    if todo.size == 0 or params.solver == 1 or params.num_cases != 1:
+        return out
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    again = _ops.optimise_beams(params.replace(solver=1), t(fixed[todo]), t(fn[todo]), t(fv[todo]), t(L[todo]))
+    out = {k: np.array(v, copy=True) for k, v in out.items()}
+    for k, v in again.items():
+        out[k][todo] = v.cpu().numpy()
+    return out
 
 
 def make_records(params: BeamOptParams, cases: Sequence[sampling.Case], out: dict) -> List[Optional[dict]]:
@@ -160,6 +214,7 @@ def generate_samples_batched(sample_indices: Sequence[int], num_nodes: int, flag
         rng = random if seed is None else random.Random(seed)
     elif seed is not None:
         raise ValueError("pass either seed or rng")
+    # (under torchrun the ranks must draw the same cases: optimise_cases checks a digest of them collectively)
     if seed is not None and rng is random:
         random.seed(seed)
     cases = [sampling.sample_case(num_nodes, flag, L, roller_nodes, available_nodes, L_max=cfg.L_max,
@@ -203,20 +258,39 @@ def generate_dataset(config: Optional[GeneratorConfig] = None, num_samples: Opti
     return training_data
 
 
+def sample_cases_packed(cfg: "GeneratorConfig", count: int, seed: int) -> "sampling.PackedCases":
+    """``count`` generate_sample() draws after ``random.seed(seed)``, natively (csrc/sampler_host.cpp: a bit-exact
+    replica of CPython's ``random`` in the reference's call order) and straight into the ABI arrays."""
+    p = cfg.params
+    rollers, available = sampling.fixed_bridge(p.num_nodes, cfg.roller_nodes)
+    s = sampling.NativeSampler(seed)
+    try:
+        return s.draw_cases(count, p.num_nodes, cfg.random_bridge, cfg.L_max, rollers, available, L_max=cfg.L_max,
+                            L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max, M_forces_max=cfg.M_forces_max,
+                            max_force=cfg.max_force, min_force=cfg.min_force, num_cases=p.num_cases,
+                            max_forces=p.max_forces)
+    finally:
+        s.close()
+
+
 def generate_columnar(config: Optional[GeneratorConfig] = None, num_samples: Optional[int] = None,
-                      seed: Optional[int] = 0, device="cuda") -> dict:
+                      seed: Optional[int] = 0, device="cuda", native_sampler: bool = True) -> dict:
     """``generate_dataset`` without the per-record Python objects: one array per key of the record
-    (``dataset.columnar_from_run``), ready for ``dataset.save_npz`` / ``save_json``.  One launch."""
+    (``dataset.columnar_from_run``), ready for ``dataset.save_npz`` / ``save_json``.  One launch.  With an integer seed
+    the cases are drawn by the native sampler (same stream, same dataset, ~70x faster than the Python loop)."""
     from . import dataset as _dataset
     cfg = config or GeneratorConfig()
     p = cfg.params
     N = cfg.num_samples if num_samples is None else num_samples
-    rollers, available = sampling.fixed_bridge(p.num_nodes, cfg.roller_nodes)
-    rng = random.Random(seed) if seed is not None else random
-    cases = [sampling.sample_case(p.num_nodes, cfg.random_bridge, cfg.L_max, rollers, available, L_max=cfg.L_max,
-                                  L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max, M_forces_max=cfg.M_forces_max,
-                                  max_force=cfg.max_force, min_force=cfg.min_force, rng=rng)
-             for _ in range(N * p.num_cases)]
+    if native_sampler and isinstance(seed, int) and 0 <= seed < 2 ** 64:
+        cases = sample_cases_packed(cfg, N * p.num_cases, seed)
+    else:
+        rollers, available = sampling.fixed_bridge(p.num_nodes, cfg.roller_nodes)
+        rng = random.Random(seed) if seed is not None else random
+        cases = [sampling.sample_case(p.num_nodes, cfg.random_bridge, cfg.L_max, rollers, available, L_max=cfg.L_max,
+                                      L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max, M_forces_max=cfg.M_forces_max,
+                                      max_force=cfg.max_force, min_force=cfg.min_force, rng=rng)
+                 for _ in range(N * p.num_cases)]
     out = optimise_cases(p, cases, device)
     return _dataset.columnar_from_run(p, cases, out)
 

@@ -130,3 +130,38 @@ def test_shard_inputs_pads_to_equal_blocks():
     assert blocks[3][0]["a"].flatten().tolist() == [9, 9, 9]
     empty = shard_inputs({"a": torch.arange(2).reshape(2, 1)}, 3, 4)
     assert empty[1] == 0 and empty[0]["a"].shape == (1, 1)
+
+
+def test_native_sampler_is_cpythons_random_bit_for_bit():
+    """csrc/sampler_host.cpp: MT19937 seeded like random.seed(int), randint / sample / choice / uniform in the
+    reference's call order (SingleCore:133-160).  Against `random` itself: raw streams (random(), randint over many
+    ranges), then > 10^5 sampled beams for both bridge modes, several seeds (incl. one beyond 32 bits), single and
+    multi-case packing -- the ABI arrays, the record metadata, and the stream position afterwards must be identical."""
+    import random
+    s = sampling.NativeSampler(12345)
+    r = random.Random(12345)
+    for i in range(200000):
+        if i % 3 == 0:
+            assert s.random() == r.random()
+        else:
+            hi = 1 + (i * 7919) % 5000
+            assert s.randint(1, hi) == r.randint(1, hi)
+    rollers, avail = sampling.fixed_bridge(101)
+    for flag, seed, nc, count in ((0, 0, 1, 60000), (1, 7, 1, 40000), (0, 2 ** 40 + 5, 4, 8000), (1, 99, 2, 8000)):
+        rng = random.Random(seed)
+        cases = [sampling.sample_case(101, flag, 200.0, rollers, avail, rng=rng) for _ in range(count)]
+        want = sampling.pack_cases(101, 4, cases, nc)
+        nat = sampling.NativeSampler(seed)
+        pc = nat.draw_cases(count, 101, flag, 200.0, rollers, avail, num_cases=nc)
+        for a, b in zip(want, pc.abi_arrays()):
+            assert np.array_equal(a, b), (flag, seed, nc)
+        assert pc.cases()[:500] == [(float(c[0]), list(c[1]), list(c[2]), list(c[3])) for c in cases[:500]]
+        assert rng.random() == nat.random()
+    # the reference goldens' draws (the reference's own statements consumed the stream of random.seed(seed))
+    from tests.helpers import goldens
+    for m, _ in goldens():
+        if m["script"] == "BO":
+            continue
+        pc = sampling.NativeSampler(m["seed"]).draw_cases(1, 101, m["flag"], 200.0, rollers, avail)
+        L, rl, ft, fvv = pc.cases()[0]
+        assert (rl, ft, fvv) == (m["roller_nodes"], m["force_nodes"], m["force_values"]) and L == m["L"]
