@@ -71,6 +71,7 @@ def select_workload(name, world):
 # outputs (I 4n, shear 4n, moment 4n, defl 8nn, rot 8nn, epochs/loss/status 12)
 BYTES_PER_BEAM = (NUM_NODES + 4 * 12 + 8) + (12 * (NUM_NODES - 1) + 16 * NUM_NODES + 12)
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12      # 64 DFMA lanes/SM x 148 SMs x max SM clock
+EXECUTED_F64_FLOP_PER_ITER = (226 * 2 + 67 + 66) * 32 // 4   # per beam-iteration, from the ncu counts (see roofline.executed_fp64)
 
 
 SOLVER = 0
@@ -83,14 +84,12 @@ def workload_params(early_stop=False):
 
 
 def sample_inputs(beams, seed):
-    import random
-    from openpystruct_b200 import sampling
+    """Seeded host sampling in the reference's draw order, by the native sampler (csrc/sampler_host.cpp:
+    the stream of random.seed(seed), bit for bit)."""
+    from openpystruct_b200 import generator
     p = workload_params()
-    rng = random.Random(seed)
-    rollers, avail = sampling.fixed_bridge(p.num_nodes, WL["rollers"])
-    cases = [sampling.sample_case(p.num_nodes, 0, 200.0, rollers, avail, rng=rng)
-             for _ in range(beams * p.num_cases)]
-    return sampling.pack_cases(p.num_nodes, p.max_forces, cases, p.num_cases)
+    cfg = generator.GeneratorConfig(params=p, roller_nodes=tuple(WL["rollers"]) if WL["rollers"] else None)
+    return generator.sample_cases_packed(cfg, beams * p.num_cases, seed).abi_arrays()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -152,11 +151,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU baselines (the oracle is only ever the thing measured HERE, never on the product path)
 # --------------------------------------------------------------------------------------------------
-def cpu_torch_port(beams, workers):
-    """The reference's torch path (port) over a process pool, MultiCore:258 pattern, E_fix = 600."""
+def cpu_torch_port(beams, workers, early_stop=False):
+    """The reference's torch path (port) over a process pool, MultiCore:258 pattern: E_fix = 600 epochs, or the
+    script's own early stopping (tolerance 5e-3, effective patience 10)."""
     from oracle import beamopt_port as port
     p = port.BeamOptParams.for_script("MC")
-    p.early_stop = False
+    p.early_stop = early_stop
     p.max_e = EPOCHS
     pool = port.PortPool(p, workers)
     try:
@@ -180,6 +180,69 @@ def cpu_c_oracle(beams, workers):
         list(ex.map(lambda c: oracle_run(p, fixed[c], fn[c], fv[c], L[c]) if len(c) else None, chunks))
     dt = time.perf_counter() - t0
     return beams / dt, dt
+
+
+def measure_config(name, beams, steps, tf_peak):
+    """Kernel-only throughput of another BASELINE config on this GPU (inputs resident, CUDA events, L2 flushed between
+    steps), for the `configs` block of the default line."""
+    import torch
+    from openpystruct_b200 import ops
+    saved = (WL, BEAMS_PER_GPU, NUM_NODES, F64_FLOP_PER_ITER, BYTES_PER_BEAM)
+    keep = WORKLOADS[name]["beams"]
+    try:
+        WORKLOADS[name]["beams"] = beams
+        select_workload(name, 1)
+        p = workload_params()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        d_in = [torch.from_numpy(a).to(dev) for a in sample_inputs(beams, seed=2000)]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        out = ops.optimise_beams(p, *d_in)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = ops.optimise_beams(p, *d_in); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        assert int(out["epochs"].min()) == EPOCHS and int(out["status"].sum()) == 0
+        tf = beams * EPOCHS * F64_FLOP_PER_ITER / (ms * 1e-3) / 1e12
+        res = {"workload": WL["name"], "beams": beams, "num_nodes": NUM_NODES, "num_cases": WL["num_cases"],
+               "value": beams / (ms * 1e-3), "unit": UNIT, "kernel_ms": ms, "flop_per_beam_iteration": F64_FLOP_PER_ITER,
+               "roofline_frac": tf / tf_peak}
+        del out, d_in, flush
+        torch.cuda.empty_cache()
+        return res
+    finally:
+        WORKLOADS[name]["beams"] = keep
+        globals().update(dict(zip(("WL", "BEAMS_PER_GPU", "NUM_NODES", "F64_FLOP_PER_ITER", "BYTES_PER_BEAM"), saved)))
+
+
+def measure_frames(steps):
+    """Frame optimiser: frames/s for a batch of random frames at a fixed epoch count."""
+    import random
+    import torch
+    from openpystruct_b200 import frames
+    p = frames.FrameOptParams(num_epochs=300, early_stop=False)
+    rng = random.Random(0)
+    batch = [frames.draw_frame(p, rng) for _ in range(592)]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nb = torch.tensor([f[0] for f in batch], dtype=torch.int32, device=dev)
+    ns = torch.tensor([f[1] for f in batch], dtype=torch.int32, device=dev)
+    frames.optimise_frames_device(p, nb, ns)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = frames.optimise_frames_device(p, nb, ns)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    assert int(out["status"].sum()) == 0 and int(out["epochs"].min()) == 300
+    return {"workload": "OpenPyStruct_FrameOpt_Discrete_Beta.py: 592 random frames (1-10 bays x 1-10 stories), 300 fixed "
+                        "epochs, one CTA per frame", "frames": len(batch), "value": len(batch) / (ms * 1e-3), "unit": "frames/s",
+            "kernel_ms": ms, "frame_epochs_per_s": len(batch) * 300 / (ms * 1e-3)}
 
 
 def host_cores():
@@ -270,7 +333,7 @@ def run_ours(args):
 
     def step():
         if peer is not None:
-            return peer.optimise(shard, rank * B)
+            return peer.optimise(shard, rank * B, check=False)       # (launch status checked once after the timed steps)
         out = ops.optimise_beams(p, *d_in)
         if world > 1:
             out = gather_outputs(out, B * world)
@@ -313,6 +376,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if peer is not None:
+        peer.check()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -375,6 +440,28 @@ def run_ours(args):
     _cabi.run_host(p, fixed, fn, fv, L, device=local)
     oneshot_value = B / (time.perf_counter() - t0)
 
+    # the call a user makes: generate_columnar = native sampling (reference draw order) + pinned session + columnar record
+    # arrays, every step from a fresh seed; sampling, H2D, kernel, D2H and the record assembly all inside the timed region
+    api = None
+    if args.workload == "cfg2" and world == 1:
+        from openpystruct_b200 import generator
+        gcfg = generator.GeneratorConfig(params=p)
+        for _ in generator.stream_columnar(gcfg, num_samples=2 * B, batch_size=B, seed=1, reuse_buffers=True):
+            pass
+        t0 = time.perf_counter()
+        recs = 0
+        for col in generator.stream_columnar(gcfg, num_samples=e2e_steps * B, batch_size=B, seed=100, reuse_buffers=True):
+            recs += int(len(col["L"]))
+            checksum = float(col["I_values"][-1, -1])                  # (touch the batch before it is recycled)
+        api = {"value": recs / (time.perf_counter() - t0), "unit": UNIT,
+               "path": "generator.stream_columnar(seed): batches of one seeded stream -- native sampler (reference draw "
+                       "order, next batch drawn on a host thread while the GPU runs) -> ops_beamopt_session_run -> columnar "
+                       "record arrays on the host (views of the pinned buffers, valid until the next batch)",
+               "records": recs, "batch": B}
+        t0 = time.perf_counter()
+        col = generator.generate_columnar(gcfg, num_samples=B, seed=7)
+        api["one_call_generate_columnar"] = B / (time.perf_counter() - t0)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -398,16 +485,28 @@ def run_ours(args):
     except Exception:
         pass
 
+    configs = None
+    if world == 1 and args.workload == "cfg2" and not args.no_configs:
+        # the other BASELINE configs and the frame optimiser on this GPU (kernel-only, few steps): driver-visible
+        configs = {"cfg3": measure_config("cfg3", 1000000, 2, tf_measured),
+                   "cfg4": measure_config("cfg4", 100000, 2, tf_measured),
+                   "cfg5": measure_config("cfg5", 100000, 2, tf_measured),
+                   "frames": measure_frames(2)}
+
     cores = host_cores()
     cpu = None
     cpu_c = None
     if not args.no_cpu_baseline and world == 1 and args.workload == "cfg2":
-        sample_beams = max(cores * 4, 16)
+        sample_beams = max(cores * 13, 208)                      # >= 200 beams
         rate, done, dt = cpu_torch_port(sample_beams, cores)
+        es_rate, es_done, es_dt = cpu_torch_port(sample_beams, cores, early_stop=True)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{done} beams x {EPOCHS} fixed epochs in {dt:.1f} s on a {cores}-process pool "
                          "(reference torch path port: real torch.sum/autograd/Adam on CPU + scipy dpbsv for "
-                         "the OpenSees half; OpenSeesPy not installable offline)"}
+                         "the OpenSees half; OpenSeesPy not installable offline)",
+               "early_stop_mode": {"value": es_rate, "unit": UNIT,
+                                   "sample": f"{es_done} beams with the MultiCore script's early stopping (tolerance 5e-3, "
+                                             f"patience 10) in {es_dt:.1f} s, same pool"}}
         c_beams = max(cores * 150, 600)
         c_rate, c_dt = cpu_c_oracle(c_beams, cores)
         cpu_c = {"value": c_rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -432,7 +531,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "path": "ops_beamopt_session_run (C ABI; pinned host buffers, H2D of the inputs + launch + D2H of the "
                         "whole record inside every step)",
-                "one_shot_run_host": oneshot_value},
+                "one_shot_run_host": oneshot_value, "api_e2e": api},
+        "configs": configs,
         "gpu_launches": args.steps,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": tf_measured, "unit": "TFLOP/s",
                      "frac": achieved_tf / tf_measured, "traffic": traffic,
@@ -440,6 +540,13 @@ def run_ours(args):
                                     f"nominal {NOMINAL_FP64_TFLOPS:.1f} TFLOP/s = 148 SM x 64 DFMA/clk x 1.965 GHz; "
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
+                     # what the three-moment kernel actually EXECUTES (ncu instruction counts of the production instance,
+                     # profiles/r02_*: 226 DFMA + 67 DMUL + 66 DADD warp instructions per 4-beam warp-epoch, padding lanes
+                     # included) -- the credited figure above is SURVEY 8d's band-LDL^T count, per the contract
+                     "executed_fp64": {"flop_per_beam_iteration": EXECUTED_F64_FLOP_PER_ITER,
+                                       "tflops": B * EPOCHS * EXECUTED_F64_FLOP_PER_ITER / (kernel_ms * 1e-3) / 1e12,
+                                       "frac": B * EPOCHS * EXECUTED_F64_FLOP_PER_ITER / (kernel_ms * 1e-3) / 1e12 / tf_measured}
+                     if args.workload in ("cfg2", "cfg3") else None,
                      "kernel": {"cfg2": "beamopt_lanes_kernel<13,100,1>", "cfg3": "beamopt_lanes_kernel<13,100,1>",
                                 "cfg4": "beamopt_lanes_kernel<13,0,8>", "cfg5": "beamopt_wide_kernel<32>"}[args.workload],
                      "kernel_ms": kernel_ms,
@@ -469,6 +576,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3 / cfg4 / cfg5 / frames sub-results")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--beams", type=int, default=0, help="override the workload's total beam count (exploration only)")
     ap.add_argument("--gather", choices=["peer", "nccl"], default="peer",

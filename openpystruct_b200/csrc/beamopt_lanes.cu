@@ -328,7 +328,19 @@ cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, con
     const bool sc = p.dest.nd > 1 || getenv("OPS_FORCE_SC") != nullptr;      // (the knob: profiling of the scatter instances on one GPU)
     if (sc && !lanes_scatter_supported(pl)) return cudaErrorInvalidValue;
     if (pl.num_cases > 1) {
-        // load cases sharing one inertia vector: the 100-element discretisation and the generic <= 104-element one
+        // load cases sharing one inertia vector: the reference's discretisation with compile-time element count and CTA
+        // size (BASELINE config 4), and the generic <= 104-element instances
+        if (pl.nfix == 100 && pl.threads == LANES_MAX_THREADS) {
+            switch (pl.num_cases) {
+            case 2: return sc ? launch_instance<13, 100, 2, LANES_MAX_THREADS, true>(k, B, p, pl, stream)
+                              : launch_instance<13, 100, 2, LANES_MAX_THREADS, false>(k, B, p, pl, stream);
+            case 4: return sc ? launch_instance<13, 100, 4, LANES_MAX_THREADS, true>(k, B, p, pl, stream)
+                              : launch_instance<13, 100, 4, LANES_MAX_THREADS, false>(k, B, p, pl, stream);
+            case 8: return sc ? launch_instance<13, 100, 8, LANES_MAX_THREADS, true>(k, B, p, pl, stream)
+                              : launch_instance<13, 100, 8, LANES_MAX_THREADS, false>(k, B, p, pl, stream);
+            default: return cudaErrorInvalidValue;
+            }
+        }
         switch (pl.num_cases * 100 + pl.epl) {
         case 204: return launch_instance<4, 0, 2>(k, B, p, pl, stream);
         case 208: return launch_instance<8, 0, 2>(k, B, p, pl, stream);

@@ -38,12 +38,18 @@ def columnar_from_run(params: BeamOptParams, cases, out: Dict[str, np.ndarray]) 
     packed = isinstance(cases, PackedCases)
     B = len(cases) // C
     keep_b = np.flatnonzero(np.asarray(out["status"][:B]) == 0)
+    all_ok = keep_b.size == B                                                # the common case: nothing to drop, no gather copies
     rec = (keep_b[:, None] * C + np.arange(C)[None, :]).reshape(-1)          # record index = beam * C + case
+    pick_b = (lambda a: np.asarray(a)[:B]) if all_ok else (lambda a: np.asarray(a)[keep_b])
+    pick_r = (lambda a: a) if all_ok else (lambda a: a[rec])
+    rep = (lambda a: a) if C == 1 else (lambda a: np.repeat(a, C, axis=0))
     nn = params.num_nodes
     if packed:
-        L = np.asarray(cases.L, np.float64)[keep_b]
-        node_positions = np.linspace(0.0, 1.0, nn)[None, :] * L[:, None] if len(L) else np.zeros((0, nn))
-        if len(L):                                                           # np.linspace(0, L, nn) bit for bit
+        L = pick_b(np.asarray(cases.L, np.float64))
+        node_positions = np.zeros((0, nn))
+        if len(L) and np.all(L == L[0]):                                     # fixed bridge: one row, broadcast (read-only view)
+            node_positions = np.broadcast_to(np.linspace(0, L[0], nn), (len(L), nn))
+        elif len(L):                                                         # np.linspace(0, L, nn) bit for bit
             step = L / (nn - 1)
             node_positions = np.arange(nn)[None, :] * step[:, None]
             node_positions[:, -1] = L
@@ -69,23 +75,24 @@ def columnar_from_run(params: BeamOptParams, cases, out: Dict[str, np.ndarray]) 
         vals = np.where(np.arange(width)[None, :] < lens[:, None], src[:, :width], pad).astype(dtype)
         return vals, lens
 
-    per_rec_np = np.repeat(node_positions, C, axis=0)
+    per_rec_np = rep(node_positions)
     col = {
-        "I_values": np.repeat(np.asarray(out["I"])[keep_b], C, axis=0),
-        "shear_forces": np.asarray(out["shear"])[keep_b].reshape(len(rec), -1),
-        "bending_moments": np.asarray(out["moment"])[keep_b].reshape(len(rec), -1),
-        "rotations": np.asarray(out["rot"])[keep_b].reshape(len(rec), -1),
-        "deflections": np.asarray(out["defl"])[keep_b].reshape(len(rec), -1),
+        "I_values": rep(pick_b(out["I"])),
+        "shear_forces": pick_b(out["shear"]).reshape(len(rec), -1),
+        "bending_moments": pick_b(out["moment"]).reshape(len(rec), -1),
+        "rotations": pick_b(out["rot"]).reshape(len(rec), -1),
+        "deflections": pick_b(out["defl"]).reshape(len(rec), -1),
         "node_positions": per_rec_np,
         "num_nodes": np.full(len(rec), nn, np.int32),
-        "L": np.repeat(L, C),
+        "L": rep(L),
     }
     if packed:
         first = (rec // C) * C                                               # supports shared by the cases of a beam
-        col["roller_nodes"], col["roller_nodes_len"] = ragged_packed(cases.roller_tags[first], None, np.int32, -1)
-        ft = cases.force_tags[rec]
+        col["roller_nodes"], col["roller_nodes_len"] = ragged_packed(
+            cases.roller_tags if (all_ok and C == 1) else cases.roller_tags[first], None, np.int32, -1)
+        ft = pick_r(cases.force_tags)
         col["force_nodes"], col["force_nodes_len"] = ragged_packed(ft, None, np.int32, -1)
-        fv = cases.force_vals.reshape(len(cases), -1)[rec]
+        fv = pick_r(cases.force_vals.reshape(len(cases), -1))
         col["force_values"], col["force_values_len"] = ragged_packed(ft, fv, np.float64, np.nan)
     else:
         rollers = lambda i: cases[(i // C) * C][1]                           # noqa: E731  (supports shared by the cases)

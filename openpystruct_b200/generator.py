@@ -75,7 +75,7 @@ def _require_cuda(device) -> torch.device:
 
 
 def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device="cuda",
-                   distributed: Optional[bool] = None) -> dict:
+                   distributed: Optional[bool] = None, copy: bool = True) -> dict:
     """Pack sampled cases, copy them to the GPU, run the fused loop, bring the results back (numpy).
 
     Under ``torchrun`` (an initialised process group with more than one rank; ``distributed=False`` opts out)
@@ -112,16 +112,17 @@ def optimise_cases(params: BeamOptParams, cases: Sequence[sampling.Case], device
             host = {k: v.cpu() for k, v in _dist.optimise_beams_sharded(params, inputs).items()}
         out = {k: v.numpy() for k, v in host.items()}
     else:
-        out = _session_run(params, fixed, fn, fv, L, dev)
+        out = _session_run(params, fixed, fn, fv, L, dev, copy)
     return _rerun_unsupported(params, out, fixed, fn, fv, L, dev)
 
 
 _sessions = {}
 
 
-def _session_run(params: BeamOptParams, fixed, fn, fv, L, dev) -> dict:
+def _session_run(params: BeamOptParams, fixed, fn, fv, L, dev, copy: bool = True) -> dict:
     """Single-GPU path through the host-buffer SESSION of the C ABI (pinned staging buffers, the record of each chunk
-    copied back under the next chunk's iterations): one cached session per (parameters, device), grown on demand."""
+    copied back under the next chunk's iterations): one cached session per (parameters, device), grown on demand.
+    ``copy=False`` hands out VIEWS of the session's pinned arrays (valid until the next run on that session)."""
     from . import _cabi
     B = int(L.shape[0])
     key = (params, dev.index)
@@ -133,7 +134,8 @@ def _session_run(params: BeamOptParams, fixed, fn, fv, L, dev) -> dict:
             _sessions.pop(next(iter(_sessions))).close()
         sess = _sessions[key] = _cabi.Session(params, max(B, 1024), device=dev.index)
     sess.load(fixed, fn, fv, L)
-    return {k: np.array(v, copy=True) for k, v in sess.run(B).items()}
+    out = sess.run(B)
+    return {k: v.copy() for k, v in out.items()} if copy else out      # (the pinned arrays are reused by the next run)
 
 
 def _require_identical_cases(fixed, fn, fv, L, dev) -> None:
@@ -293,6 +295,43 @@ def generate_columnar(config: Optional[GeneratorConfig] = None, num_samples: Opt
                  for _ in range(N * p.num_cases)]
     out = optimise_cases(p, cases, device)
     return _dataset.columnar_from_run(p, cases, out)
+
+
+def stream_columnar(config: Optional[GeneratorConfig] = None, num_samples: Optional[int] = None, batch_size: int = 10000,
+                    seed: int = 0, device="cuda", reuse_buffers: bool = False):
+    """``main()`` of the generators as a PIPELINE (MultiCore:246-262 loops over batches too): yields the columnar record
+    arrays of consecutive batches of one seeded stream; the cases of batch i + 1 are drawn (native sampler, its own
+    thread -- ctypes releases the GIL) while the GPU optimises batch i.  The concatenation of the batches is
+    ``generate_columnar(config, num_samples, seed)``.  ``reuse_buffers=True``: the record arrays alias the session's pinned
+    host buffers and are valid until the next batch is requested (write them out / consume them first)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import dataset as _dataset
+    cfg = config or GeneratorConfig()
+    p = cfg.params
+    N = cfg.num_samples if num_samples is None else num_samples
+    rollers, available = sampling.fixed_bridge(p.num_nodes, cfg.roller_nodes)
+    sampler = sampling.NativeSampler(seed)
+
+    def draw(count):
+        return sampler.draw_cases(count * p.num_cases, p.num_nodes, cfg.random_bridge, cfg.L_max, rollers, available,
+                                  L_max=cfg.L_max, L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max,
+                                  M_forces_max=cfg.M_forces_max, max_force=cfg.max_force, min_force=cfg.min_force,
+                                  num_cases=p.num_cases, max_forces=p.max_forces)
+
+    sizes = [min(batch_size, N - s) for s in range(0, N, batch_size)]
+    with ThreadPoolExecutor(1) as pool:
+        try:
+            nxt = pool.submit(draw, sizes[0]) if sizes else None
+            for i in range(len(sizes)):
+                cases = nxt.result()
+                nxt = pool.submit(draw, sizes[i + 1]) if i + 1 < len(sizes) else None
+                out = optimise_cases(p, cases, device, copy=not reuse_buffers)
+                yield _dataset.columnar_from_run(p, cases, out)
+        finally:
+            if nxt is not None:
+                nxt.cancel()
+            pool.shutdown(wait=True)
+            sampler.close()
 
 
 def save_training_data(training_data: dict, path: str = "training_data_PINN_mini.json") -> None:

@@ -65,6 +65,28 @@ def main():
     assert len(a["I_values"]) == int((single["status"] == 0).sum())
     if rank == 0:
         print(f"multi_gpu_check ok: generate_columnar / optimise_cases under torchrun == single GPU ({world} GPUs)", flush=True)
+    # a configuration whose kernel has no scatter instance (banded LDL^T solver) with an EMPTY shard on the last rank
+    # (one beam): every rank must take the NCCL fall-back together -- no hang, no uninitialised rows
+    p1 = cfg.params.replace(solver=1, max_e=20)
+    one = generator.optimise_cases(p1, cases[:1], dev)
+    ref1 = generator.optimise_cases(p1, cases[:1], dev, distributed=False)
+    for k in ref1:
+        assert np.array_equal(one[k], ref1[k]), (rank, "empty shard fall-back", k)
+    few = generator.optimise_cases(cfg.params.replace(max_e=20), cases[:world - 1], dev)      # scatter path, last rank empty
+    ref2 = generator.optimise_cases(cfg.params.replace(max_e=20), cases[:world - 1], dev, distributed=False)
+    for k in ref2:
+        assert np.array_equal(few[k], ref2[k]), (rank, "empty shard scatter", k)
+    # ranks that sampled DIFFERENT cases (an unseeded `random` per process) are an error on every rank, not a silently
+    # corrupted dataset
+    rng_r = random.Random(100 + rank)
+    mine = [sampling.sample_case(cfg.params.num_nodes, 0, cfg.L_max, rollers, avail, rng=rng_r) for _ in range(8)]
+    try:
+        generator.optimise_cases(cfg.params.replace(max_e=5), mine, dev)
+        raise AssertionError("differing cases were accepted")
+    except RuntimeError as ex:
+        assert "sampled different cases" in str(ex), ex
+    if rank == 0:
+        print(f"multi_gpu_check ok: empty shards, collective fall-back, differing-cases check ({world} GPUs)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

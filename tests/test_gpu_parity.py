@@ -525,3 +525,43 @@ def test_other_discretisations(num_nodes, solver):
     assert (a["loss"][same] == b["loss"][same]).mean() > 0.95
     assert rel_err(b["moment"][same, 0], a["moment"][same, 0]).max() < 1e-6
     assert rel_err(b["defl"][same, 0], a["defl"][same, 0]).max() < 1e-6
+
+
+def test_native_sampler_paths_and_the_pipelined_stream():
+    """The native sampler draws the stream of `random` (CPU test): through the GPU the columnar dataset of
+    generate_columnar(seed) equals the one built from the Python sampler's cases, and the pipelined batches of
+    stream_columnar concatenate to it -- with copies and with views of the session's pinned buffers."""
+    cfg = generator.GeneratorConfig.multi_core()
+    p = cfg.params.replace(max_e=60)
+    cfg = generator.GeneratorConfig(params=p)
+    want = generator.generate_columnar(cfg, num_samples=1000, seed=11, native_sampler=False)
+    got = generator.generate_columnar(cfg, num_samples=1000, seed=11)
+    for k in want:
+        assert np.array_equal(np.asarray(want[k]), np.asarray(got[k]), equal_nan=True), k
+    for reuse in (False, True):
+        parts = []
+        for col in generator.stream_columnar(cfg, num_samples=1000, batch_size=384, seed=11, reuse_buffers=reuse):
+            parts.append({k: np.array(v, copy=True) for k, v in col.items()})
+        assert [len(c["L"]) for c in parts] == [384, 384, 232]
+        for k in ("I_values", "deflections", "rotations", "shear_forces", "bending_moments", "L", "node_positions"):
+            assert np.array_equal(np.concatenate([c[k] for c in parts]), np.asarray(want[k])), (k, reuse)
+        fv = np.concatenate([np.pad(c["force_values"], ((0, 0), (0, 4 - c["force_values"].shape[1])), constant_values=np.nan)
+                             for c in parts])
+        wv = np.pad(want["force_values"], ((0, 0), (0, 4 - want["force_values"].shape[1])), constant_values=np.nan)
+        assert np.array_equal(fv, wv, equal_nan=True)
+
+
+def test_more_than_five_rollers_are_rerun_with_the_band_solver():
+    """The reference's ops.fix loop takes any number of rollers (SingleCore:101-102); the three-moment kernels take five.
+    The host entry re-runs such beams with the banded LDL^T solver instead of dropping them."""
+    p = BeamOptParams.for_script("SC").replace(max_e=30)
+    cases = seeded_cases(p, 6, seed=9) + [(200.0, [10, 20, 30, 40, 50, 60], [55], [-1e5]),
+                                          (200.0, [5, 15, 25, 45, 65, 85, 100], [50, 70], [-2e5, -1e5])]
+    out = generator.optimise_cases(p, cases)
+    assert not out["status"].any()
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    a = oracle_run(p, fixed, fn, fv, L)
+    assert np.array_equal(a["epochs"], out["epochs"])
+    assert np.max(np.abs(a["I"] - out["I"]) / a["I"]) < 1e-5
+    recs = generator.make_records(p, cases, out)
+    assert all(r is not None for r in recs) and recs[-1]["roller_nodes"] == [5, 15, 25, 45, 65, 85, 100]
