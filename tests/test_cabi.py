@@ -102,3 +102,18 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("no cpu fallback", ""), os.path.join(dirpath, f)
                 assert "hostsim" not in text or f.endswith(".cuh"), os.path.join(dirpath, f)
+
+
+def test_no_packed_product_was_contracted_into_a_packed_sum():
+    """ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under -fmad=false, which would change torch's
+    rounding; the lanes kernel is written so that it cannot happen, and scripts/sass_packed_audit.py proves it for the
+    built library by counting the packed instructions of every kernel instance (no GPU needed: cuobjdump)."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_packed_audit.py"), build.build()],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "packed audit: PASS" in r.stdout, r.stdout[-3000:]
+    assert r.stdout.count("ok ") >= 20

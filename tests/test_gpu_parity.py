@@ -565,3 +565,31 @@ def test_more_than_five_rollers_are_rerun_with_the_band_solver():
     assert np.max(np.abs(a["I"] - out["I"]) / a["I"]) < 1e-5
     recs = generator.make_records(p, cases, out)
     assert all(r is not None for r in recs) and recs[-1]["roller_nodes"] == [5, 15, 25, 45, 65, 85, 100]
+
+
+def test_the_ctypes_stub_of_INTEGRATION_md_runs_as_printed():
+    """INTEGRATION.md section B is what a maintainer of the reference pastes into a script: the code block is taken
+    from the document as printed, executed (no package import, no torch), and its records compared with the package path."""
+    import os
+    import re
+    from tests.helpers import ROOT
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "class BeamOptimiser" in b)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        exec(compile(block, "INTEGRATION.md", "exec"), ns)
+        p = BeamOptParams.for_script("SC")
+        cases = seeded_cases(p, 300, seed=21)
+        opt = ns["BeamOptimiser"](max_beams=512)
+        got = {k: np.array(v, copy=True) for k, v in opt(cases).items()}
+        again = opt(cases[:77])                               # a second batch on the same session
+        assert np.array_equal(again["I"], got["I"][:77])
+        opt.close()
+    finally:
+        os.chdir(cwd)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    want = gpu_run(p, fixed, fn, fv, L)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
