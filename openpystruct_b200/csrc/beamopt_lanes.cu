@@ -51,15 +51,25 @@ __device__ __forceinline__ void team_sync(unsigned team_mask, int barrier_id)
         const long long row = p.row0 + b, rowc = row * NC + case_id; /* dataset rows of the beam / its load case */  \
         lane_emit_forces<EPL>(n, rg, ls, gs, fb.invLe, l, fields, p.shear + rowc * n, p.moment + rowc * n);          \
         if (l == 0) {                                                                                                \
-            LaneStore ls0 = ls;                                                                                      \
-            group_emit_displacements(k, fb, ls0, gs, fields, p.defl + rowc * nn, p.rot + rowc * nn);                 \
+            if constexpr (NC == 1) {                                                                                 \
+                const ParkedInertia parked = {reinterpret_cast<const float *>(ls.scr), ls.ls};                       \
+                group_emit_displacements(k, fb, gs, fields, parked, p.defl + rowc * nn, p.rot + rowc * nn);          \
+            } else {                                                                                                 \
+                group_emit_displacements(k, fb, gs, fields,                                                          \
+                                         [&](int e) { return (double)team_inertia<NC>(ls, 0, case_id, e, 0); },      \
+                                         p.defl + rowc * nn, p.rot + rowc * nn);                                     \
+            }                                                                                                        \
             if (case_id == 0) {                                                                                      \
                 p.epochs[row] = t;                                                                                   \
                 p.loss[row] = lossf;                                                                                 \
                 p.status[row] = bad;                                                                                 \
             }                                                                                                        \
         }                                                                                                            \
-        if (case_id == 0) lane_emit_inertias<EPL>(n, rg, l, p.I_values + row * n);                                   \
+        if constexpr (NC == 1) lane_emit_inertias<EPL>(n, rg, l, p.I_values + row * n);                              \
+        else if (case_id == 0) {                                                                                     \
+            _Pragma("unroll") for (int kk = 0; kk < EPL; ++kk)                                                       \
+                if (LPB * kk + l < n) p.I_values[row * n + LPB * kk + l] = team_inertia<NC>(ls, l, 0, LPB * kk + l, t > 0 ? 3 : 0); \
+        }                                                                                                            \
         if (SC && p.dest.nd > 1) { /* dataset gather: every lane re-reads rows other lanes wrote */                  \
             __syncwarp(gmask);                                                                                       \
             lane_copy_record(n, nn, l, p.dest, row, rowc, case_id == 0);                                             \
@@ -104,6 +114,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     ls.mq = reinterpret_cast<Pair *>(lane_d) + tid;
     ls.scr = lane_d + (size_t)2 * EPL * T + tid;
     ls.xc = reinterpret_cast<PairF *>(lane_d + (size_t)(2 * EPL + SCR_SLOTS) * T) + tid;
+    ls.xb = lane_d + (size_t)(2 * EPL + SCR_SLOTS + EPL) * T + tid;
     GroupStore gs;
     gs.gs = GS;
     gs.tab = tab_d + (size_t)TAB_SLOTS * g;
@@ -180,9 +191,13 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                 pc = pass1_consts(fb);
                 if (!bad) {
                     lane_init<EPL>(k, n, fb, gs, ls, l, rg);
-                    lane_pass1<EPL>(rg, ls, pc, false);
+                    if (NC == 1) lane_pass1<EPL>(rg, ls, pc, false);
                 } else {
                     lane_reset<EPL>(k, rg);
+                }
+                if constexpr (NC > 1) {
+                    team_init<EPL, NC>(k, n, ls, l, case_id, rg);   // (bad beams too: the record emits I_0)
+                    team_sync<NC>(team_mask, barrier_id);           // the owners' rows are read by every group of the team
                 }
             } else {
                 exhausted = true;
@@ -200,21 +215,29 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             neg_step = __ldg(p.sched + 2 * t);
             bc2_sqrt = __ldg(p.sched + 2 * t + 1);
         }
+        if constexpr (NC > 1) {
+            if (run) team_pass1<EPL, NC>(rg, ls, pc, case_id);      // P1: this case's sums from the team's inertias
+        }
         __syncwarp();
         if (run) lane_reduce(l, fb.m, ls, gs);
         __syncwarp();
         if (run) rc = group_solve(fb, gs, l);
         __syncwarp();
-        if (NC > 1) {
-            if (run) lane_case_squares<EPL>(rg, ls, gs, fb.invLe);
-            if (NC * LPB <= 32) __syncwarp();
-            else if (run) team_sync<NC>(team_mask, barrier_id);    // whole warps belong to one team: uniform
-        }
         // this epoch may be the beam's last: the pass parks the inertias it starts from for the record
         const bool stage_I = run && ((t + 1 >= k.max_epochs) || (k.early_stop && counter + 1 >= k.patience));
-        if (run) lane_pass<EPL, NC, NBK>(k, n, rg, ls, gs, pc, fb.invLe, l, case_id, neg_step, bc2_sqrt, stage_I);
-        if (NC * LPB <= 32) __syncwarp();                           // (NC > 1: exchange columns are rewritten next epoch)
-        else if (run) team_sync<NC>(team_mask, barrier_id);
+        if constexpr (NC == 1) {
+            if (run) lane_pass<EPL, NC, NBK>(k, n, rg, ls, gs, pc, fb.invLe, l, case_id, neg_step, bc2_sqrt, stage_I);
+            __syncwarp();
+        } else {
+            if (run) lane_case_squares<EPL>(rg, ls, gs, fb.invLe);
+            if (NC * LPB <= 32) __syncwarp();
+            else if (run) team_sync<NC>(team_mask, barrier_id);     // whole warps belong to one team: uniform
+            if (run) team_owner_update<EPL, NC>(k, rg, ls, case_id, neg_step, bc2_sqrt);     // P2
+            if (NC * LPB <= 32) __syncwarp();
+            else if (run) team_sync<NC>(team_mask, barrier_id);
+            if (run) team_loss_sums<EPL, NC>(n, ls, l, case_id);                              // P3
+            __syncwarp();
+        }
         if (run) {
             lossf = group_loss(k, n, ls, l);
             ++t;
@@ -228,7 +251,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
         }
         if (have && done) {
             OPS_RECORD_PATH
-        } else if (stage_I) {
+        } else if (NC == 1 && stage_I) {
             lane_pass1<EPL>(rg, ls, pc, true);                      // the beam goes on: the sums the parked inertias displaced
         }
     }

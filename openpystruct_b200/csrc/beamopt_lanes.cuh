@@ -59,7 +59,13 @@ constexpr int GX_INTS = 6;                      // m, last, nloads, setup status
 constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + GX_DOUBLES;   // strided [slot][group] columns (+ TAB_SLOTS contiguous)
 constexpr int GROUP_INTS = FlexStore::NUM_INTS + GX_INTS;
 
-OPS_HD constexpr int lane_doubles(int epl, int nc) { return 2 * epl + SCR_SLOTS + (nc > 1 ? epl : 0); }
+// multi-case teams: pair j of the lane's slots is OWNED by group j % NC (its fp32 chain, Adam state and exchange rows)
+OPS_HD constexpr int team_owned_pairs(int epl, int nc) { return ((epl + 1) / 2 + nc - 1) / nc; }
+constexpr int XB_ROWS = 4;                      // exchange rows of an owned pair: {I_old, d, q, I_new}, one fp32 pair each
+OPS_HD constexpr int lane_doubles(int epl, int nc)
+{
+    return 2 * epl + SCR_SLOTS + (nc > 1 ? epl + XB_ROWS * team_owned_pairs(epl, nc) : 0);
+}
 
 template <int EPL>
 struct LaneRegs {
@@ -105,6 +111,7 @@ struct LaneStore {
     Pair *mq;                                   // [EPL]: {M0, Q0} of the element
     double *scr;                                // [SCR_SLOTS]
     PairF *xc;                                  // [EPL] (multi-case kernels only): squares exchanged between the case groups
+    double *xb;                                 // [XB_ROWS * owned pairs] (multi-case): the owner's rows of its pairs
     long ls;
 };
 
@@ -433,6 +440,70 @@ OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, cons
     }
 }
 
+// The fp32 half of one batch of slot pairs, stage by stage (used by the single-case pass and by the owners of a team).
+// In scope: OPS_P ("for every live pair i of the batch"), k, one, half and the per-pair arrays
+// I, c, h (inputs) -> d, q, g (outputs), scratch nb, y, rb, s, gg, rgg, rs, db, qg, t0, t1, t2.  Stages:
+//   nb = -(2E I + eps) ; y ~ 1 / sqrt(I)            rb = refined 1 / b ; s = sqrt(I)
+//   d = c / b ; gg = Gf (kf s) ; rs = 1 / s          db = d / b ; rgg = refined 1 / gg ; rs = RN(1 / s)
+//   q = h / gg ; bending branch gb = ((-am) db) E2   qg = q / gg
+//   shear branch gs = ((((-as) qg) Gf) kf) (0.5 / s) ; g = (1 + gs) + gb   (sums of products: scalar adds, fastmath.cuh)
+#define OPS_FP32_CHAIN \
+        OPS_P { nb[i] = fm::mul2_add(I[i], splat(-k.E2), splat(-k.epsf)); y[i] = fm::rsq2_a(I[i]); } \
+        OPS_P { rb[i] = fm::rcp2_a(neg2(nb[i])); t0[i] = mul2(I[i], y[i]); y[i] = mul2(y[i], half); } \
+        OPS_P { t1[i] = fma2(nb[i], rb[i], one); t2[i] = fma2(neg2(t0[i]), t0[i], I[i]); } \
+        OPS_P { rb[i] = fma2(rb[i], t1[i], rb[i]); s[i] = fma2(t2[i], y[i], t0[i]); } \
+        OPS_P { t0[i] = mul2(c[i], rb[i]); gg[i] = mul2(splat(k.kf), s[i]); rs[i] = fm::rcp2_a(s[i]); } \
+        OPS_P { t1[i] = fma2(nb[i], t0[i], c[i]); gg[i] = mul2(splat(k.Gf), gg[i]); t2[i] = fma2(neg2(s[i]), rs[i], one); } \
+        OPS_P { d[i] = fma2(rb[i], t1[i], t0[i]); rgg[i] = fm::rcp2_a(gg[i]); rs[i] = fma2(rs[i], t2[i], rs[i]); } \
+        OPS_P { t0[i] = mul2(d[i], rb[i]); t1[i] = fma2(neg2(gg[i]), rgg[i], one); t2[i] = fma2(neg2(s[i]), rs[i], one); } \
+        OPS_P { db[i] = fma2(nb[i], t0[i], d[i]); rgg[i] = fma2(rgg[i], t1[i], rgg[i]); rs[i] = fma2(rs[i], t2[i], rs[i]); } \
+        OPS_P { db[i] = fma2(rb[i], db[i], t0[i]); t1[i] = mul2(h[i], rgg[i]); rs[i] = mul2(half, rs[i]); } \
+        OPS_P { db[i] = mul2(splat(-k.am), db[i]); t2[i] = fma2(neg2(gg[i]), t1[i], h[i]); } \
+        OPS_P { db[i] = mul2(db[i], splat(k.E2)); q[i] = fma2(rgg[i], t2[i], t1[i]); } \
+        OPS_P t0[i] = mul2(q[i], rgg[i]); \
+        OPS_P t1[i] = fma2(neg2(gg[i]), t0[i], q[i]); \
+        OPS_P qg[i] = fma2(rgg[i], t1[i], t0[i]); \
+        OPS_P qg[i] = mul2(splat(-k.as_), qg[i]); \
+        OPS_P qg[i] = mul2(qg[i], splat(k.Gf)); \
+        OPS_P qg[i] = mul2(qg[i], splat(k.kf)); \
+        OPS_P qg[i] = fm::mul2_add(qg[i], rs[i], one); \
+        OPS_P g[i] = fm::f2(qg[i].x + db[i].x, qg[i].y + db[i].y);
+
+// Adam's m, v, the step and the clamp for the batch (element_update_f32, second half).  In scope besides the above:
+// rg, p0, neg_step, bc2_sqrt, rbc; reads I[i], g[i]; leaves the stepped inertias in rg.I[p0 + i].
+//   sqrt(v) / bc2_sqrt + eps ; I + (neg_step m) / denom ; clamp   (t0 is finite: den > 0, v and m finite; v is never
+//   NaN here: the loss was finite).  v below the fast square root's range: the generic operators (cold).
+#define OPS_ADAM_STEP \
+        F2 vmin = splat(3.0e38f); \
+        OPS_P { t0[i] = add2(g[i], neg2(rg.m[p0 + i])); t1[i] = mul2(splat(k.omb2f), g[i]); t2[i] = mul2(rg.v[p0 + i], splat(k.b2f)); } \
+        OPS_P { rg.m[p0 + i] = fma2(splat(k.w1), t0[i], rg.m[p0 + i]); rg.v[p0 + i] = fma2(t1[i], g[i], t2[i]); } \
+        OPS_P { vmin.x = fminf(vmin.x, rg.v[p0 + i].x); vmin.y = fminf(vmin.y, rg.v[p0 + i].y); } \
+        if (fminf(vmin.x, vmin.y) >= fm::SQRT_F_MIN) { \
+            F2 den[NB], rd[NB], num[NB]; \
+            OPS_P y[i] = fm::rsq2_a(rg.v[p0 + i]); \
+            OPS_P { t0[i] = mul2(rg.v[p0 + i], y[i]); y[i] = mul2(y[i], half); num[i] = mul2(splat(neg_step), rg.m[p0 + i]); } \
+            OPS_P t1[i] = fma2(neg2(t0[i]), t0[i], rg.v[p0 + i]); \
+            OPS_P t0[i] = fma2(t1[i], y[i], t0[i]); \
+            OPS_P t1[i] = mul2(t0[i], splat(rbc)); \
+            OPS_P den[i] = fma2(splat(-bc2_sqrt), t1[i], t0[i]); \
+            OPS_P den[i] = fma2(splat(rbc), den[i], t1[i]); \
+            OPS_P den[i] = add2(den[i], splat(k.adam_epsf)); \
+            OPS_P rd[i] = fm::rcp2_a(den[i]); \
+            OPS_P t0[i] = fma2(neg2(den[i]), rd[i], one); \
+            OPS_P rd[i] = fma2(rd[i], t0[i], rd[i]); \
+            OPS_P t0[i] = mul2(num[i], rd[i]); \
+            OPS_P t1[i] = fma2(neg2(den[i]), t0[i], num[i]); \
+            OPS_P t0[i] = fma2(rd[i], t1[i], t0[i]); \
+            OPS_P t0[i] = add2(I[i], t0[i]); \
+            OPS_P rg.I[p0 + i] = fm::f2(fmaxf(t0[i].x, k.clampf), fmaxf(t0[i].y, k.clampf)); \
+        } else { \
+            OPS_P { \
+                const float dx = sqrtf(rg.v[p0 + i].x) / bc2_sqrt + k.adam_epsf, dy = sqrtf(rg.v[p0 + i].y) / bc2_sqrt + k.adam_epsf; \
+                const float xx = I[i].x + (neg_step * rg.m[p0 + i].x) / dx, xy = I[i].y + (neg_step * rg.m[p0 + i].y) / dy; \
+                rg.I[p0 + i] = fm::f2(xx < k.clampf ? k.clampf : xx, xy < k.clampf ? k.clampf : xy); \
+            } \
+        }
+
 // torch.sum partials of one quantity: the four ILP rows as two packed pairs {row 0, row 1}, {row 2, row 3}, and the
 // scalar tail.  Pair j = slots 2 j, 2 j + 1 falls on rows (0, 1) or (2, 3) of the 4-row block, so inside the block
 // one packed add per pair keeps every row's own summation order.
@@ -535,71 +606,14 @@ OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneS
                 }
             }
         }
-        // nb = -(2E I + eps) ; y ~ 1 / sqrt(I)
-        OPS_P { nb[i] = fm::mul2_add(I[i], splat(-k.E2), splat(-k.epsf)); y[i] = fm::rsq2_a(I[i]); }
-        // rb = refined 1 / b ; s = sqrt(I)
-        OPS_P { rb[i] = fm::rcp2_a(neg2(nb[i])); t0[i] = mul2(I[i], y[i]); y[i] = mul2(y[i], half); }
-        OPS_P { t1[i] = fma2(nb[i], rb[i], one); t2[i] = fma2(neg2(t0[i]), t0[i], I[i]); }
-        OPS_P { rb[i] = fma2(rb[i], t1[i], rb[i]); s[i] = fma2(t2[i], y[i], t0[i]); }
-        // d = c / b ; gg = Gf (kf s) ; rs = 1 / s
-        OPS_P { t0[i] = mul2(c[i], rb[i]); gg[i] = mul2(splat(k.kf), s[i]); rs[i] = fm::rcp2_a(s[i]); }
-        OPS_P { t1[i] = fma2(nb[i], t0[i], c[i]); gg[i] = mul2(splat(k.Gf), gg[i]); t2[i] = fma2(neg2(s[i]), rs[i], one); }
-        OPS_P { d[i] = fma2(rb[i], t1[i], t0[i]); rgg[i] = fm::rcp2_a(gg[i]); rs[i] = fma2(rs[i], t2[i], rs[i]); }
-        // db = d / b ; rgg = refined 1 / gg ; rs = RN(1 / s)
-        OPS_P { t0[i] = mul2(d[i], rb[i]); t1[i] = fma2(neg2(gg[i]), rgg[i], one); t2[i] = fma2(neg2(s[i]), rs[i], one); }
-        OPS_P { db[i] = fma2(nb[i], t0[i], d[i]); rgg[i] = fma2(rgg[i], t1[i], rgg[i]); rs[i] = fma2(rs[i], t2[i], rs[i]); }
-        OPS_P { db[i] = fma2(rb[i], db[i], t0[i]); t1[i] = mul2(h[i], rgg[i]); rs[i] = mul2(half, rs[i]); }
-        // q = h / gg ; bending branch gb = ((-am) db) E2
-        OPS_P { db[i] = mul2(splat(-k.am), db[i]); t2[i] = fma2(neg2(gg[i]), t1[i], h[i]); }
-        OPS_P { db[i] = mul2(db[i], splat(k.E2)); q[i] = fma2(rgg[i], t2[i], t1[i]); }
-        // qg = q / gg
-        OPS_P t0[i] = mul2(q[i], rgg[i]);
-        OPS_P t1[i] = fma2(neg2(gg[i]), t0[i], q[i]);
-        OPS_P qg[i] = fma2(rgg[i], t1[i], t0[i]);
-        // shear branch gs = ((((-as) qg) Gf) kf) (0.5 / s) ; g = (1 + gs) + gb  (sums of products: scalar adds, fastmath.cuh)
-        OPS_P qg[i] = mul2(splat(-k.as_), qg[i]);
-        OPS_P qg[i] = mul2(qg[i], splat(k.Gf));
-        OPS_P qg[i] = mul2(qg[i], splat(k.kf));
-        OPS_P qg[i] = fm::mul2_add(qg[i], rs[i], one);
-        OPS_P g[i] = fm::f2(qg[i].x + db[i].x, qg[i].y + db[i].y);
+        OPS_FP32_CHAIN
         OPS_P {
             sum_pair<EPL>(aI, sh, p0 + i, l, I[i]); sum_pair<EPL>(ad, sh, p0 + i, l, d[i]); sum_pair<EPL>(aq, sh, p0 + i, l, q[i]);
         }
         if (stage_I) {
             OPS_P *reinterpret_cast<F2 *>(ls.scr + (long)(p0 + i) * ls.ls) = I[i];
         }
-        // Adam: m, v
-        F2 vmin = splat(3.0e38f);
-        OPS_P { t0[i] = add2(g[i], neg2(rg.m[p0 + i])); t1[i] = mul2(splat(k.omb2f), g[i]); t2[i] = mul2(rg.v[p0 + i], splat(k.b2f)); }
-        OPS_P { rg.m[p0 + i] = fma2(splat(k.w1), t0[i], rg.m[p0 + i]); rg.v[p0 + i] = fma2(t1[i], g[i], t2[i]); }
-        OPS_P { vmin.x = fminf(vmin.x, rg.v[p0 + i].x); vmin.y = fminf(vmin.y, rg.v[p0 + i].y); }   // (v is never NaN here: the loss was finite)
-        if (fminf(vmin.x, vmin.y) >= fm::SQRT_F_MIN) {
-            F2 den[NB], rd[NB], num[NB];
-            // sqrt(v) / bc2_sqrt + eps
-            OPS_P y[i] = fm::rsq2_a(rg.v[p0 + i]);
-            OPS_P { t0[i] = mul2(rg.v[p0 + i], y[i]); y[i] = mul2(y[i], half); num[i] = mul2(splat(neg_step), rg.m[p0 + i]); }
-            OPS_P t1[i] = fma2(neg2(t0[i]), t0[i], rg.v[p0 + i]);
-            OPS_P t0[i] = fma2(t1[i], y[i], t0[i]);                  // sqrt(v)
-            OPS_P t1[i] = mul2(t0[i], splat(rbc));
-            OPS_P den[i] = fma2(splat(-bc2_sqrt), t1[i], t0[i]);
-            OPS_P den[i] = fma2(splat(rbc), den[i], t1[i]);
-            OPS_P den[i] = add2(den[i], splat(k.adam_epsf));
-            // I + (neg_step m) / denom, clamp
-            OPS_P rd[i] = fm::rcp2_a(den[i]);
-            OPS_P t0[i] = fma2(neg2(den[i]), rd[i], one);
-            OPS_P rd[i] = fma2(rd[i], t0[i], rd[i]);
-            OPS_P t0[i] = mul2(num[i], rd[i]);
-            OPS_P t1[i] = fma2(neg2(den[i]), t0[i], num[i]);
-            OPS_P t0[i] = fma2(rd[i], t1[i], t0[i]);
-            OPS_P t0[i] = add2(I[i], t0[i]);
-            OPS_P rg.I[p0 + i] = fm::f2(fmaxf(t0[i].x, k.clampf), fmaxf(t0[i].y, k.clampf));   // (t0 is finite: den > 0, v and m finite)
-        } else {
-            OPS_P {
-                const float dx = sqrtf(rg.v[p0 + i].x) / bc2_sqrt + k.adam_epsf, dy = sqrtf(rg.v[p0 + i].y) / bc2_sqrt + k.adam_epsf;
-                const float xx = I[i].x + (neg_step * rg.m[p0 + i].x) / dx, xy = I[i].y + (neg_step * rg.m[p0 + i].y) / dy;
-                rg.I[p0 + i] = fm::f2(xx < k.clampf ? k.clampf : xx, xy < k.clampf ? k.clampf : xy);
-            }
-        }
+        OPS_ADAM_STEP
         // flexibility sums of the next epoch
         {
             double Id[2 * NB], r[2 * NB], e[2 * NB];
@@ -621,6 +635,151 @@ OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneS
     st[0] = sum_rows(aI); st[1] = aI.tail;
     st[fs_] = sum_rows(ad); st[fs_ + 1] = ad.tail;
     st[2 * fs_] = sum_rows(aq); st[2 * fs_ + 1] = aq.tail;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Load cases sharing one inertia vector: the team's division of labour.
+//
+// The NC groups of a team (one per load case) used to carry identical I, m, v and to repeat the whole fp32 half.
+// Now slot pair j of a lane belongs to ONE group, its owner j % NC: only the owner runs the pair's fp32 chain and
+// Adam step and keeps its m, v; what the others need travels through the owner's exchange rows {I_old, d, q, I_new}
+// (XB_ROWS fp32 pairs per owned pair, in the owner's lane column).  Per epoch, separated by team barriers:
+//   P1 (every group, its own case): flexibility sums from I_new of ALL pairs (team_pass1), reduction, support moments,
+//      M^2 and V^2 of its case for all slots into the squares exchange (lane_case_squares);
+//   P2 (owners): squares summed over the cases in case order -> loss terms, gradient, Adam, clamp -> exchange rows;
+//   P3 (every group, redundantly: the stop decision must be the same everywhere): torch.sum partials of I_old, d, q
+//      over all pairs -> loss.
+// Nothing else of the state lives in registers, and the record reads I_old / I_new from the exchange.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+OPS_HD fm::F2 *team_row(const LaneStore &ls, int case_id, int j, int f)
+{
+    return reinterpret_cast<fm::F2 *>(ls.xb + ((long)(j % NC) - case_id) * LPB + (long)((j / NC) * XB_ROWS + f) * ls.ls);
+}
+
+// once per beam (after lane_init): the owned pairs start from I_0, their exchange rows likewise
+template <int EPL, int NC>
+OPS_HD void team_init(const BeamConsts &k, int n, const LaneStore &ls, int l, int case_id, LaneRegs<EPL> &rg)
+{
+    constexpr int NP = LaneRegs<EPL>::NP, NPO = team_owned_pairs(EPL, NC);
+#pragma unroll
+    for (int p_ = 0; p_ < NPO; ++p_) {
+        const int j = case_id + p_ * NC;
+        const int e0 = LPB * (2 * j) + l, e1 = LPB * (2 * j + 1) + l;
+        const fm::F2 I0 = fm::f2((2 * j < EPL && e0 < n) ? k.I0f : 1.0f, (2 * j + 1 < EPL && e1 < n) ? k.I0f : 1.0f);
+        rg.I[p_] = I0; rg.m[p_] = fm::splat(0.0f); rg.v[p_] = fm::splat(0.0f);
+        if (j < NP) {
+            fm::F2 *row = reinterpret_cast<fm::F2 *>(ls.xb + (long)(p_ * XB_ROWS) * ls.ls);
+            row[0] = I0;
+            *reinterpret_cast<fm::F2 *>(ls.xb + (long)(p_ * XB_ROWS + 1) * ls.ls) = fm::splat(0.0f);
+            *reinterpret_cast<fm::F2 *>(ls.xb + (long)(p_ * XB_ROWS + 2) * ls.ls) = fm::splat(0.0f);
+            *reinterpret_cast<fm::F2 *>(ls.xb + (long)(p_ * XB_ROWS + 3) * ls.ls) = I0;
+        }
+    }
+}
+
+// P1: the five sums of this group's case from the team's current inertias (stage-major batches of six slots)
+template <int EPL, int NC>
+OPS_HD void team_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, int case_id)
+{
+    constexpr int SB = 6;
+    SpanSums acc = {0.0, 0.0, 0.0, 0.0, 0.0};
+#define OPS_T _Pragma("unroll") for (int s_ = 0; s_ < SB; ++s_) if (k0 + s_ < EPL)
+#pragma unroll
+    for (int k0 = 0; k0 < EPL; k0 += SB) {
+        double Id[SB], r[SB], e[SB], ke[SB];
+        Pair mq[SB];
+        OPS_T {
+            const int kk = k0 + s_;
+            const fm::F2 In = *team_row<NC>(ls, case_id, kk >> 1, 3);
+            Id[s_] = (double)((kk & 1) ? In.y : In.x);
+            mq[s_] = ls.mq[(long)kk * ls.ls];
+            ke[s_] = slot_ke<EPL>(rg, kk);
+        }
+        OPS_T r[s_] = fm::rcp64_a(Id[s_]);
+        OPS_T e[s_] = fma(-Id[s_], r[s_], 1.0);
+        OPS_T e[s_] = fma(e[s_], e[s_], e[s_]);
+        OPS_T r[s_] = fma(r[s_], e[s_], r[s_]);
+        OPS_T pass1_accumulate<EPL>(rg, ls, pc, k0 + s_, r[s_], ke[s_], mq[s_], true, acc);
+    }
+#undef OPS_T
+}
+
+// P2: the owner's pairs -- squares of all cases, fp32 chain, Adam, exchange rows
+template <int EPL, int NC>
+OPS_HD void team_owner_update(const BeamConsts &k, LaneRegs<EPL> &rg, const LaneStore &ls, int case_id, float neg_step,
+                              float bc2_sqrt)
+{
+    using fm::F2; using fm::splat; using fm::neg2; using fm::mul2; using fm::add2; using fm::fma2;
+    constexpr int NP = LaneRegs<EPL>::NP, NB = team_owned_pairs(EPL, NC), p0 = 0;
+    const PairF *x0 = ls.xc - (long)case_id * LPB;             // this lane's column in the team's case-0 group
+    const F2 one = splat(1.0f), half = splat(0.5f);
+    const float rbc = fm::rcp_r(bc2_sqrt);
+    F2 I[NB], c[NB], h[NB], nb[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB], g[NB];
+    F2 t0[NB], t1[NB], t2[NB];
+#define OPS_P _Pragma("unroll") for (int i = 0; i < NB; ++i)
+    OPS_P {
+        const int j = case_id + i * NC;
+        I[i] = rg.I[i];
+        c[i] = splat(0.0f); h[i] = splat(0.0f);
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs) {
+            const int kk = 2 * j + hs;
+            if (j < NP && kk < EPL) {
+                PairF x = x0[(long)kk * ls.ls];
+                float cs = x.c, hq = x.h;
+#pragma unroll
+                for (int cc = 1; cc < NC; ++cc) {
+                    x = x0[(long)kk * ls.ls + cc * LPB];
+                    cs += x.c; hq += x.h;
+                }
+                if (hs) { c[i].y = cs; h[i].y = hq; } else { c[i].x = cs; h[i].x = hq; }
+            }
+        }
+    }
+    OPS_FP32_CHAIN
+    { OPS_ADAM_STEP }
+    OPS_P {
+        const int j = case_id + i * NC;
+        if (j < NP) {
+            *reinterpret_cast<F2 *>(ls.xb + (long)(i * XB_ROWS + 0) * ls.ls) = I[i];
+            *reinterpret_cast<F2 *>(ls.xb + (long)(i * XB_ROWS + 1) * ls.ls) = d[i];
+            *reinterpret_cast<F2 *>(ls.xb + (long)(i * XB_ROWS + 2) * ls.ls) = q[i];
+            *reinterpret_cast<F2 *>(ls.xb + (long)(i * XB_ROWS + 3) * ls.ls) = rg.I[i];
+        }
+    }
+#undef OPS_P
+}
+
+// P3: torch.sum partials of sum I, sum d, sum q over ALL pairs of the lane, from the owners' rows
+template <int EPL, int NC>
+OPS_HD void team_loss_sums(int n, const LaneStore &ls, int l, int case_id)
+{
+    constexpr int NP = LaneRegs<EPL>::NP;
+    const SumShape sh = sum_shape(n);
+    SumAcc aI = {fm::splat(0.0f), fm::splat(0.0f), 0.0f}, ad = aI, aq = aI;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        sum_pair<EPL>(aI, sh, j, l, *team_row<NC>(ls, case_id, j, 0));
+        sum_pair<EPL>(ad, sh, j, l, *team_row<NC>(ls, case_id, j, 1));
+        sum_pair<EPL>(aq, sh, j, l, *team_row<NC>(ls, case_id, j, 2));
+    }
+    float *st = reinterpret_cast<float *>(ls.scr + (long)SCR_STAGE * ls.ls);
+    const long fs_ = 2 * ls.ls;
+    st[0] = sum_rows(aI); st[1] = aI.tail;
+    st[fs_] = sum_rows(ad); st[fs_ + 1] = ad.tail;
+    st[2 * fs_] = sum_rows(aq); st[2 * fs_ + 1] = aq.tail;
+}
+
+// inertia of element e of the beam from the exchange rows (f = 0: last analysed, f = 3: after the last step), read by
+// ANY lane of the group (lane 0's displacement march, the emission of I_values): lane ln's column is ln further on
+template <int NC>
+OPS_HD float team_inertia(const LaneStore &ls, int lane_of_reader, int case_id, int e, int f)
+{
+    const int kk = e >> 3, ln = e & (LPB - 1), j = kk >> 1;
+    const fm::F2 v = *reinterpret_cast<const fm::F2 *>(ls.xb + (ln - lane_of_reader) + ((long)(j % NC) - case_id) * LPB +
+                                                        (long)((j / NC) * XB_ROWS + f) * ls.ls);
+    return (kk & 1) ? v.y : v.x;
 }
 
 // total loss in torch's order: scalar tail first, then the eight vector lanes (every lane, redundantly)
@@ -661,10 +820,21 @@ OPS_HD void lane_emit_forces(int n, const LaneRegs<EPL> &rg, const LaneStore &ls
     }
 }
 
-// lane 0: displacements by integrating the curvature (flex_deflections_march) from the inertias the beam's last pass
-// parked in the scratch columns (pair j of a lane = float pair at slot j)
-OPS_HD void group_emit_displacements(const BeamConsts &k, const FlexBeam &fb, const LaneStore &ls0,
-                                     const GroupStore &gs, bool fields, double *defl, double *rot)
+// the inertias the beam's last pass parked in the scratch columns (pair j of a lane = float pair at slot j), seen from lane 0
+struct ParkedInertia {
+    const float *stage;
+    long ls;
+    OPS_HD double operator()(int e) const
+    {
+        const int kk = e >> 3, ln = e & (LPB - 1);
+        return (double)stage[(long)(kk >> 1) * 2 * ls + 2 * ln + (kk & 1)];
+    }
+};
+
+// lane 0: displacements by integrating the curvature (flex_deflections_march); `inertia(e)` = the last analysed I_e
+template <class InertiaFn>
+OPS_HD void group_emit_displacements(const BeamConsts &k, const FlexBeam &fb, const GroupStore &gs, bool fields, InertiaFn inertia,
+                                     double *defl, double *rot)
 {
     const int nn = k.nn;
     if (!fields) {
@@ -679,11 +849,6 @@ OPS_HD void group_emit_displacements(const BeamConsts &k, const FlexBeam &fb, co
         gs.fs.ms(j) = gs.tab[2 * j];
     }
     gs.fs.ms(m) = fb.Moh;
-    const float *stage = reinterpret_cast<const float *>(ls0.scr);
-    auto inertia = [&](int e) {
-        const int kk = e >> 3, ln = e & (LPB - 1);
-        return (double)stage[(long)(kk >> 1) * 2 * ls0.ls + 2 * ln + (kk & 1)];
-    };
     flex_deflections_march(k, fb, gs.fs, inertia, [&](int i, double u, double th) {
         const bool z = k.zero_last_node && i == nn - 1;
         defl[i] = z ? 0.0 : u;

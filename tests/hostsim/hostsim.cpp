@@ -229,6 +229,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
     std::vector<Pair> lane_p((size_t)EPL * TL);
     std::vector<double> lane_s((size_t)SCR_SLOTS * TL), grp_d((size_t)GROUP_DOUBLES * NC);
     std::vector<PairF> lane_x((size_t)EPL * TL);
+    std::vector<double> lane_b((size_t)XB_ROWS * team_owned_pairs(EPL, NC) * TL);
     std::vector<Pair> tab_p((size_t)TAB_SLOTS / 2 * NC);
     std::vector<int> grp_i((size_t)GROUP_INTS * NC);
     LaneStore ls[NC][LPB];
@@ -240,6 +241,7 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             ls[c][l].mq = lane_p.data() + col;
             ls[c][l].scr = lane_s.data() + col;
             ls[c][l].xc = lane_x.data() + col;
+            ls[c][l].xb = lane_b.data() + col;
         }
         gs[c].gs = NC;
         gs[c].tab = reinterpret_cast<double *>(tab_p.data()) + (size_t)TAB_SLOTS * c;
@@ -266,8 +268,11 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             group_table_init(gs[c]);
             bad = group_fetch(k, L[b], gs[c], fb[c]);
             for (int l = 0; l < LPB; ++l) {
-                if (!bad) { lane_init<EPL>(k, n, fb[c], gs[c], ls[c][l], l, rg[c][l]); lane_pass1<EPL>(rg[c][l], ls[c][l], pass1_consts(fb[c]), false); }
-                else lane_reset<EPL>(k, rg[c][l]);
+                if (!bad) {
+                    lane_init<EPL>(k, n, fb[c], gs[c], ls[c][l], l, rg[c][l]);
+                    if (NC == 1) lane_pass1<EPL>(rg[c][l], ls[c][l], pass1_consts(fb[c]), false);
+                } else lane_reset<EPL>(k, rg[c][l]);
+                if constexpr (NC > 1) team_init<EPL, NC>(k, n, ls[c][l], l, c, rg[c][l]);
             }
         }
         int t = 0, counter = 0;
@@ -277,6 +282,10 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
         while (!done) {
             neg_step = sched[2 * t]; bc2_sqrt = sched[2 * t + 1];
             int rc = 0;
+            if constexpr (NC > 1) {
+                for (int c = 0; c < NC; ++c)
+                    for (int l = 0; l < LPB; ++l) team_pass1<EPL, NC>(rg[c][l], ls[c][l], pass1_consts(fb[c]), c);
+            }
             for (int c = 0; c < NC; ++c) {
                 for (int l = 0; l < LPB; ++l) lane_reduce(l, fb[c].m, ls[c][l], gs[c]);
                 for (int l = LPB - 1; l >= 0; --l) rc |= group_solve(fb[c], gs[c], l);
@@ -284,10 +293,16 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
             }
             float lv[NC][LPB];
             const bool stage_I = (t + 1 >= k.max_epochs) || (k.early_stop && counter + 1 >= k.patience);
-            for (int c = 0; c < NC; ++c)
+            if constexpr (NC == 1) {
                 for (int l = 0; l < LPB; ++l)
-                    lane_pass<EPL, NC>(k, n, rg[c][l], ls[c][l], gs[c], pass1_consts(fb[c]), fb[c].invLe, l, c, neg_step, bc2_sqrt,
+                    lane_pass<EPL, NC>(k, n, rg[0][l], ls[0][l], gs[0], pass1_consts(fb[0]), fb[0].invLe, l, 0, neg_step, bc2_sqrt,
                                        stage_I);
+            } else {
+                for (int c = 0; c < NC; ++c)
+                    for (int l = 0; l < LPB; ++l) team_owner_update<EPL, NC>(k, rg[c][l], ls[c][l], c, neg_step, bc2_sqrt);
+                for (int c = 0; c < NC; ++c)
+                    for (int l = 0; l < LPB; ++l) team_loss_sums<EPL, NC>(n, ls[c][l], l, c);
+            }
             for (int c = 0; c < NC; ++c)
                 for (int l = 0; l < LPB; ++l) lv[c][l] = group_loss(k, n, ls[c][l], l);
             for (int c = 0; c < NC; ++c)
@@ -301,18 +316,25 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
                 if (counter >= k.patience) done = true;
             }
             if (t >= k.max_epochs) done = true;
-            if (!done && stage_I)
-                for (int c = 0; c < NC; ++c)
-                    for (int l = 0; l < LPB; ++l) lane_pass1<EPL>(rg[c][l], ls[c][l], pass1_consts(fb[c]), true);
+            if (NC == 1 && !done && stage_I)
+                for (int l = 0; l < LPB; ++l) lane_pass1<EPL>(rg[0][l], ls[0][l], pass1_consts(fb[0]), true);
         }
         const bool fields = (t > 0) && (bad == 0);
         for (int c = 0; c < NC; ++c) {
             const int64_t bc = b * NC + c;
             for (int l = 0; l < LPB; ++l)
                 lane_emit_forces<EPL>(n, rg[c][l], ls[c][l], gs[c], fb[c].invLe, l, fields, shear + bc * n, moment + bc * n);
-            group_emit_displacements(k, fb[c], ls[c][0], gs[c], fields, defl + bc * nn, rot + bc * nn);
-            for (int l = 0; l < LPB; ++l)
-                if (c == 0) lane_emit_inertias<EPL>(n, rg[c][l], l, I_values + b * n);
+            if constexpr (NC == 1) {
+                const ParkedInertia parked = {reinterpret_cast<const float *>(ls[c][0].scr), ls[c][0].ls};
+                group_emit_displacements(k, fb[c], gs[c], fields, parked, defl + bc * nn, rot + bc * nn);
+                for (int l = 0; l < LPB; ++l) lane_emit_inertias<EPL>(n, rg[c][l], l, I_values + b * n);
+            } else {
+                group_emit_displacements(k, fb[c], gs[c], fields,
+                                         [&](int e) { return (double)team_inertia<NC>(ls[c][0], 0, c, e, 0); },
+                                         defl + bc * nn, rot + bc * nn);
+                if (c == 0)
+                    for (int e = 0; e < n; ++e) I_values[b * n + e] = team_inertia<NC>(ls[0][0], 0, 0, e, t > 0 ? 3 : 0);
+            }
         }
         epochs[b] = t; loss[b] = lossf; status[b] = bad;
     }
