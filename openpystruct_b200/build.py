@@ -9,7 +9,7 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libopenpystruct_b200.so")
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("beamopt_kernels.cu", "beamopt_lanes.cu", "beamopt_wide.cu", "frameopt.cu", "sampler_host.cpp")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("beamopt_kernels.cu", "beamopt_lanes.cu", "beamopt_lanes_tm.cu", "beamopt_wide.cu", "frameopt.cu", "sampler_host.cpp")]
 HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("beamopt_core.cuh", "beamopt_flex.cuh", "beamopt_lanes.cuh", "beamopt_wide.cuh",
                                                    "beamopt_internal.cuh", "fastmath.cuh")] + \
           [os.path.join(os.path.dirname(_PKG), "include", "openpystruct_b200.h")]

@@ -40,11 +40,15 @@ struct LanesPlan {
     int num_cases;       // load cases per beam = groups per team
     int threads, blocks;
     size_t smem_bytes;
+    int tm;              // tensor-memory instance (beamopt_lanes_tm.cu): {M0, Q0}, m, v of a lane in TMEM, 17 warps per SM
 };
 bool lanes_supported(const BeamConsts &k, int num_cases);
 bool lanes_scatter_supported(const LanesPlan &pl);
 int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_optin, LanesPlan *pl);
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream);
+bool lanes_tm_supported(int epl, int num_cases);
+int lanes_tm_plan(int64_t B, int sms, int smem_optin, LanesPlan *pl);
+cudaError_t lanes_tm_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream);
 
 // shared-memory-state three-moment kernels, 8 or 32 lanes per beam (beamopt_wide.cu)
 struct WidePlan {

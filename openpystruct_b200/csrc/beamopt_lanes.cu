@@ -277,6 +277,17 @@ int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_
     pl->epl = pick_epl(k.n);
     pl->nfix = (k.n == 100) ? 100 : 0;
     pl->num_cases = num_cases;
+    pl->tm = 0;
+    // Tensor-memory instance (beamopt_lanes_tm.cu): 64 beams per SM and round instead of 40.  Measured (profiles/
+    // r02_tensor_memory_instance.md): its epoch is slower per warp (128 registers), so it wins exactly where it turns two
+    // rounds of this instance into one -- fixed epoch counts with 52..64 beams per SM (+6 % .. +19 %).
+    // OPS_LANES_TM = 0 / 1 forces the choice (profiling knob; same results either way).
+    {
+        const char *tm_env = getenv("OPS_LANES_TM");
+        const int64_t per_sm = (B + sms - 1) / sms;
+        const bool want_tm = tm_env ? atoi(tm_env) != 0 : (!k.early_stop && per_sm >= 52 && per_sm <= 64);
+        if (want_tm && lanes_tm_supported(pl->epl, num_cases) && lanes_tm_plan(B, sms, smem_optin, pl) == 0) return 0;
+    }
     const size_t per_group = (size_t)LPB * 8 * lane_doubles(pl->epl, num_cases) + (size_t)(TAB_SLOTS + GROUP_DOUBLES) * 8 +
                              (size_t)GROUP_INTS * 4;
     int groups = (int)((size_t)smem_optin / per_group);
@@ -323,6 +334,7 @@ bool lanes_scatter_supported(const LanesPlan &pl) { return pl.num_cases == 1 || 
 // development build (kernel iteration on the reference's discretisation only: compiles in a fraction of the time)
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream)
 {
+    if (pl.tm) return lanes_tm_launch(k, B, p, pl, stream);
     if (pl.num_cases != 1 || pl.nfix != 100 || p.dest.nd > 1) return cudaErrorInvalidValue;
     if (pl.threads == LANES_MAX_THREADS) return launch_instance<13, 100, 1, LANES_MAX_THREADS, false>(k, B, p, pl, stream);
     if (pl.threads == LANES_BIG_THREADS) return launch_instance<13, 100, 1, LANES_BIG_THREADS, false>(k, B, p, pl, stream);
@@ -348,6 +360,7 @@ static cudaError_t launch_single_case(const BeamConsts &k, long long B, const Op
 
 cudaError_t lanes_launch(const BeamConsts &k, long long B, const OptPtrs &p, const LanesPlan &pl, cudaStream_t stream)
 {
+    if (pl.tm) return lanes_tm_launch(k, B, p, pl, stream);
     const bool sc = p.dest.nd > 1 || getenv("OPS_FORCE_SC") != nullptr;      // (the knob: profiling of the scatter instances on one GPU)
     if (sc && !lanes_scatter_supported(pl)) return cudaErrorInvalidValue;
     if (pl.num_cases > 1) {

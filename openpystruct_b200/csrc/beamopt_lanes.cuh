@@ -124,6 +124,231 @@ struct GroupStore {
     long gs;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Where a lane keeps what only IT ever touches: the statics {M0, Q0} of its elements and Adam's m, v.
+//
+// HomeShared (every instance but the tensor-memory one): {M0, Q0} in the lane's shared-memory column, m and v in
+// LaneRegs.  HomeTm (beamopt_lanes_tm.cu): both in TENSOR MEMORY -- the 256 KB per SM next to the tensor cores that
+// this path otherwise leaves idle -- through tcgen05.st / tcgen05.ld (32x32b: thread t of a warp owns TMEM lane
+// 32 (warp % 4) + t, the warps sharing a lane quarter own disjoint column blocks).  That takes 1.7 KB per beam out of
+// shared memory and 28 registers out of every thread, which is what lets 17 warps = 68 beams stay resident per SM
+// instead of 10.  Tensor-memory instructions are WARP-COLLECTIVE (.sync.aligned): every function that
+// touches a HomeTm is called by all 32 lanes of a warp, and the lanes whose group has nothing to do compute on whatever
+// their columns hold and keep the results to themselves (`active` arguments below).
+// Column layout of a lane (32-bit words): [4 kk, 4 kk + 4) = {M0, Q0} of slot kk (kk < 2 NP), then
+// [8 NP + 4 j, 8 NP + 4 j + 4) = {m.x, m.y, v.x, v.y} of pair j.
+// Host build (tests/hostsim): the same layout in a plain array per lane.
+// ---------------------------------------------------------------------------------------------
+OPS_HD void words_of(double d, unsigned int &lo, unsigned int &hi)
+{
+#if defined(__CUDA_ARCH__)
+    lo = (unsigned int)__double2loint(d); hi = (unsigned int)__double2hiint(d);
+#else
+    unsigned long long u; memcpy(&u, &d, 8); lo = (unsigned int)u; hi = (unsigned int)(u >> 32);
+#endif
+}
+OPS_HD double double_of(unsigned int lo, unsigned int hi)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    const unsigned long long u = ((unsigned long long)hi << 32) | lo; double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+OPS_HD unsigned int word_of(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    unsigned int u; memcpy(&u, &f, 4); return u;
+#endif
+}
+OPS_HD float float_of(unsigned int u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+struct HomeShared {
+    static constexpr bool TM = false;
+    OPS_HD void wait_loads() const {}
+    OPS_HD void wait_stores() const {}
+    // {M0, Q0} of slots k0 .. k0 + N - 1 (those < EPL)
+    template <int EPL, int N>
+    OPS_HD void fetch_mq(const LaneStore &ls, int k0, Pair (&mq)[N]) const
+    {
+#pragma unroll
+        for (int s = 0; s < N; ++s) if (k0 + s < EPL) mq[s] = ls.mq[(long)(k0 + s) * ls.ls];
+    }
+    template <int EPL, int N>
+    OPS_HD void fetch_mv(const LaneRegs<EPL> &rg, int p0, fm::F2 (&m)[N], fm::F2 (&v)[N]) const
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (p0 + i < LaneRegs<EPL>::NP) { m[i] = rg.m[p0 + i]; v[i] = rg.v[p0 + i]; }
+    }
+    template <int EPL, int N>
+    OPS_HD void put_mv(LaneRegs<EPL> &rg, int p0, const fm::F2 (&m)[N], const fm::F2 (&v)[N]) const
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (p0 + i < LaneRegs<EPL>::NP) { rg.m[p0 + i] = m[i]; rg.v[p0 + i] = v[i]; }
+    }
+    // lane_init: {M0, Q0} of slot kk
+    OPS_HD void stage_mq(const LaneStore &ls, int kk, const Pair &mq) const { ls.mq[(long)kk * ls.ls] = mq; }
+};
+
+struct HomeTm {
+    static constexpr bool TM = true;
+    unsigned int base;                          // device: tensor-memory address of the lane's first column (lane quarter of the warp in bits 16+)
+    unsigned int *w;                            // host simulator: the lane's words
+    template <int N>
+    OPS_HD void ld(int col, unsigned int (&r)[N]) const
+    {
+        static_assert(N == 4 || N == 8 || N == 16, "tcgen05.ld.32x32b.xN");
+#if defined(__CUDA_ARCH__)
+        const unsigned int a = base + (unsigned int)col;
+        if constexpr (N == 4)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+        else if constexpr (N == 8)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a));
+        else
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(a));
+#else
+        for (int i = 0; i < N; ++i) r[i] = w[col + i];
+#endif
+    }
+    template <int N>
+    OPS_HD void st(int col, const unsigned int (&r)[N]) const
+    {
+        static_assert(N == 4 || N == 8, "tcgen05.st.32x32b.xN");
+#if defined(__CUDA_ARCH__)
+        const unsigned int a = base + (unsigned int)col;
+        if constexpr (N == 4)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0, %1, %2, %3};"
+                         ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(a) : "memory");
+        else
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+                         ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(a) : "memory");
+#else
+        for (int i = 0; i < N; ++i) w[col + i] = r[i];
+#endif
+    }
+    OPS_HD void wait_loads() const
+    {
+#if defined(__CUDA_ARCH__)
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
+    }
+    OPS_HD void wait_stores() const
+    {
+#if defined(__CUDA_ARCH__)
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+    }
+    // words [c0, c0 + 4 NQ) as NQ quads, with the widest loads
+    template <int NQ>
+    OPS_HD void ld_quads(int c0, unsigned int (&q)[NQ][4]) const
+    {
+        static_assert(NQ >= 1 && NQ <= 6, "batch size");
+        if constexpr (NQ >= 4) {
+            unsigned int r[16];
+            ld<16>(c0, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i >> 2][i & 3] = r[i];
+            if constexpr (NQ == 5) ld<4>(c0 + 16, q[4]);
+            if constexpr (NQ == 6) {
+                unsigned int t[8];
+                ld<8>(c0 + 16, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) q[4 + (i >> 2)][i & 3] = t[i];
+            }
+        } else if constexpr (NQ >= 2) {
+            unsigned int r[8];
+            ld<8>(c0, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i >> 2][i & 3] = r[i];
+            if constexpr (NQ == 3) ld<4>(c0 + 8, q[2]);
+        } else {
+            ld<4>(c0, q[0]);
+        }
+    }
+    template <int EPL, int N>
+    OPS_HD void fetch_mq(const LaneStore &, int k0, Pair (&mq)[N]) const
+    {
+        unsigned int q[N][4];
+        ld_quads<N>(4 * k0, q);                 // (slots up to 2 NP - 1 have columns; the padding slot reads zeros)
+        wait_loads();
+#pragma unroll
+        for (int s = 0; s < N; ++s) { mq[s].x = double_of(q[s][0], q[s][1]); mq[s].y = double_of(q[s][2], q[s][3]); }
+    }
+    template <int EPL, int N>
+    OPS_HD void fetch_mv(const LaneRegs<EPL> &, int p0, fm::F2 (&m)[N], fm::F2 (&v)[N]) const
+    {
+        unsigned int q[N][4];
+        ld_quads<N>(8 * LaneRegs<EPL>::NP + 4 * p0, q);
+        wait_loads();
+#pragma unroll
+        for (int i = 0; i < N; ++i) { m[i] = fm::f2(float_of(q[i][0]), float_of(q[i][1])); v[i] = fm::f2(float_of(q[i][2]), float_of(q[i][3])); }
+    }
+    template <int EPL, int N>
+    OPS_HD void put_mv(LaneRegs<EPL> &, int p0, const fm::F2 (&m)[N], const fm::F2 (&v)[N]) const
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (p0 + i < LaneRegs<EPL>::NP) {
+                const unsigned int r[4] = {word_of(m[i].x), word_of(m[i].y), word_of(v[i].x), word_of(v[i].y)};
+                st<4>(8 * LaneRegs<EPL>::NP + 4 * (p0 + i), r);
+            }
+        }
+    }
+    // lane_init stages {M0, Q0} in the lane's scratch column (slots 2 kk, 2 kk + 1); tm_commit moves them over
+    OPS_HD void stage_mq(const LaneStore &ls, int kk, const Pair &mq) const
+    {
+        ls.scr[(long)(2 * kk) * ls.ls] = mq.x; ls.scr[(long)(2 * kk + 1) * ls.ls] = mq.y;
+    }
+    static OPS_HD constexpr int columns(int epl) { return 12 * ((epl + 1) / 2); }
+};
+
+// New beams of some groups of the warp (`fresh` lanes; called by ALL lanes): the staged {M0, Q0} and m = v = 0 go to
+// tensor memory; a store writes all 32 lanes, so the other lanes write back what they hold (read-modify-write); the
+// fresh lanes' scratch columns are cleared for the partial sums.
+template <int EPL>
+OPS_HD void tm_commit(const HomeTm &hm, const LaneStore &ls, bool fresh)
+{
+    constexpr int NP = LaneRegs<EPL>::NP;
+    hm.wait_stores();
+#pragma unroll
+    for (int kk = 0; kk < 2 * NP; ++kk) {
+        unsigned int r[4];
+        hm.ld<4>(4 * kk, r);
+        hm.wait_loads();
+        if (fresh) {
+            double M0 = 0.0, Q0 = 0.0;
+            if (kk < EPL) { M0 = ls.scr[(long)(2 * kk) * ls.ls]; Q0 = ls.scr[(long)(2 * kk + 1) * ls.ls]; }
+            words_of(M0, r[0], r[1]); words_of(Q0, r[2], r[3]);
+        }
+        hm.st<4>(4 * kk, r);
+    }
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        unsigned int r[4];
+        hm.ld<4>(8 * NP + 4 * j, r);
+        hm.wait_loads();
+        if (fresh) { r[0] = 0u; r[1] = 0u; r[2] = 0u; r[3] = 0u; }
+        hm.st<4>(8 * NP + 4 * j, r);
+    }
+    hm.wait_stores();
+    if (fresh) {
+        for (int s = 0; s < SCR_SLOTS; ++s) ls.scr[(long)s * ls.ls] = 0.0;
+    }
+}
+
 // torch.sum layout of an n-vector over slots k (beamopt_core.cuh): k < blk -> 4 ILP rows,
 // blk <= k < vec -> row 0, k == vec -> scalar tail (lanes l < ntail)
 struct SumShape {
@@ -165,9 +390,9 @@ OPS_HD int group_fetch(const BeamConsts &k, double L, const GroupStore &gs, Flex
     return gs.gi[3 * gs.gs];
 }
 
-template <int EPL>
+template <int EPL, class HM = HomeShared>
 OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const GroupStore &gs, const LaneStore &ls,
-                      int l, LaneRegs<EPL> &rg)
+                      int l, LaneRegs<EPL> &rg, const HM &hm = HM())
 {
     constexpr int NP = LaneRegs<EPL>::NP;
     const int m = fb.m, last = fb.last, nl = fb.nloads;
@@ -226,7 +451,7 @@ OPS_HD void lane_init(const BeamConsts &k, int n, const FlexBeam &fb, const Grou
         slot_ref<EPL>(rg.I, kk) = I0; slot_ref<EPL>(rg.m, kk) = 0.0f; slot_ref<EPL>(rg.v, kk) = 0.0f;
         rg.ke[kk >> 2] |= (unsigned int)kei << (8 * (kk & 3));
         Pair mq; mq.x = M0; mq.y = Q0;
-        ls.mq[(long)kk * ls.ls] = mq;
+        hm.stage_mq(ls, kk, mq);
     }
     if (EPL & 1) { rg.I[NP - 1].y = 1.0f; rg.m[NP - 1].y = 0.0f; rg.v[NP - 1].y = 0.0f; }     // the pair's padding half
     if (prev != DUMMY) ends |= 1u << (EPL - 1);
@@ -296,19 +521,30 @@ OPS_HD void pass1_accumulate(const LaneRegs<EPL> &rg, const LaneStore &ls, const
 
 // the sums on their own: first epoch of a beam (parked = false), and after an epoch whose pass parked the inertias
 // in the first slots of the scratch column instead (those slots are cleared first: a lane only ever writes the
-// partials of the spans it touches, the others must read zero)
-template <int EPL>
-OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, bool parked)
+// partials of the spans it touches, the others must read zero).  HomeTm: called by the whole warp, the lanes that
+// are not `active` leave their scratch column alone.
+template <int EPL, class HM = HomeShared>
+OPS_HD void lane_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, bool parked, const HM &hm = HM(),
+                       bool active = true)
 {
-    if (parked) {
+    if (parked && active) {
 #pragma unroll
         for (int j = 0; j < LaneRegs<EPL>::NP; ++j) ls.scr[(long)j * ls.ls] = 0.0;
     }
     SpanSums a = {0.0, 0.0, 0.0, 0.0, 0.0};
+    constexpr int SB = HM::TM ? 4 : 1;          // slots per fetch
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) {
-        const float If = (kk & 1) ? rg.I[kk >> 1].y : rg.I[kk >> 1].x;
-        pass1_accumulate<EPL>(rg, ls, pc, kk, fm::rcp64((double)If), slot_ke<EPL>(rg, kk), ls.mq[(long)kk * ls.ls], true, a);
+    for (int k0 = 0; k0 < EPL; k0 += SB) {
+        Pair mq[SB];
+        hm.template fetch_mq<EPL, SB>(ls, k0, mq);
+#pragma unroll
+        for (int s_ = 0; s_ < SB; ++s_) {
+            const int kk = k0 + s_;
+            if (kk < EPL) {
+                const float If = (kk & 1) ? rg.I[kk >> 1].y : rg.I[kk >> 1].x;
+                pass1_accumulate<EPL>(rg, ls, pc, kk, fm::rcp64((double)If), slot_ke<EPL>(rg, kk), mq[s_], active, a);
+            }
+        }
     }
 }
 
@@ -406,13 +642,18 @@ OPS_HD void group_table_init(const GroupStore &gs)
 
 // bending moment (three-moment sign: sagging positive) and shear at the node-i end of slot kk
 template <int EPL>
+OPS_HD void element_forces_mq(const LaneRegs<EPL> &rg, const GroupStore &gs, double invLe, int kk, const Pair &mq,
+                              double &Mc, double &Qv)
+{
+    const Pair lo = table_row(gs.tab, row_offset(rg.spans, kk));
+    Mc = fma(lo.y, slot_ke<EPL>(rg, kk), mq.x + lo.x);
+    Qv = fma(lo.y, invLe, mq.y);
+}
+template <int EPL>
 OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe, int kk,
                            double &Mc, double &Qv)
 {
-    const Pair lo = table_row(gs.tab, row_offset(rg.spans, kk));
-    const Pair mq = ls.mq[(long)kk * ls.ls];
-    Mc = fma(lo.y, slot_ke<EPL>(rg, kk), mq.x + lo.x);
-    Qv = fma(lo.y, invLe, mq.y);
+    element_forces_mq<EPL>(rg, gs, invLe, kk, ls.mq[(long)kk * ls.ls], Mc, Qv);
 }
 
 // Slots are processed in batches of NBP PAIRS, STAGE BY STAGE across the batch: the stages of one element are a
@@ -470,19 +711,20 @@ OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, cons
         OPS_P g[i] = fm::f2(qg[i].x + db[i].x, qg[i].y + db[i].y);
 
 // Adam's m, v, the step and the clamp for the batch (element_update_f32, second half).  In scope besides the above:
-// rg, p0, neg_step, bc2_sqrt, rbc; reads I[i], g[i]; leaves the stepped inertias in rg.I[p0 + i].
+// rg, p0, neg_step, bc2_sqrt, rbc and the batch's Adam state m_[i], v_[i] (updated in place); reads I[i], g[i];
+// leaves the stepped inertias in rg.I[p0 + i].
 //   sqrt(v) / bc2_sqrt + eps ; I + (neg_step m) / denom ; clamp   (t0 is finite: den > 0, v and m finite; v is never
 //   NaN here: the loss was finite).  v below the fast square root's range: the generic operators (cold).
 #define OPS_ADAM_STEP \
         F2 vmin = splat(3.0e38f); \
-        OPS_P { t0[i] = add2(g[i], neg2(rg.m[p0 + i])); t1[i] = mul2(splat(k.omb2f), g[i]); t2[i] = mul2(rg.v[p0 + i], splat(k.b2f)); } \
-        OPS_P { rg.m[p0 + i] = fma2(splat(k.w1), t0[i], rg.m[p0 + i]); rg.v[p0 + i] = fma2(t1[i], g[i], t2[i]); } \
-        OPS_P { vmin.x = fminf(vmin.x, rg.v[p0 + i].x); vmin.y = fminf(vmin.y, rg.v[p0 + i].y); } \
+        OPS_P { t0[i] = add2(g[i], neg2(m_[i])); t1[i] = mul2(splat(k.omb2f), g[i]); t2[i] = mul2(v_[i], splat(k.b2f)); } \
+        OPS_P { m_[i] = fma2(splat(k.w1), t0[i], m_[i]); v_[i] = fma2(t1[i], g[i], t2[i]); } \
+        OPS_P { vmin.x = fminf(vmin.x, v_[i].x); vmin.y = fminf(vmin.y, v_[i].y); } \
         if (fminf(vmin.x, vmin.y) >= fm::SQRT_F_MIN) { \
             F2 den[NB], rd[NB], num[NB]; \
-            OPS_P y[i] = fm::rsq2_a(rg.v[p0 + i]); \
-            OPS_P { t0[i] = mul2(rg.v[p0 + i], y[i]); y[i] = mul2(y[i], half); num[i] = mul2(splat(neg_step), rg.m[p0 + i]); } \
-            OPS_P t1[i] = fma2(neg2(t0[i]), t0[i], rg.v[p0 + i]); \
+            OPS_P y[i] = fm::rsq2_a(v_[i]); \
+            OPS_P { t0[i] = mul2(v_[i], y[i]); y[i] = mul2(y[i], half); num[i] = mul2(splat(neg_step), m_[i]); } \
+            OPS_P t1[i] = fma2(neg2(t0[i]), t0[i], v_[i]); \
             OPS_P t0[i] = fma2(t1[i], y[i], t0[i]); \
             OPS_P t1[i] = mul2(t0[i], splat(rbc)); \
             OPS_P den[i] = fma2(splat(-bc2_sqrt), t1[i], t0[i]); \
@@ -498,8 +740,8 @@ OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, cons
             OPS_P rg.I[p0 + i] = fm::f2(fmaxf(t0[i].x, k.clampf), fmaxf(t0[i].y, k.clampf)); \
         } else { \
             OPS_P { \
-                const float dx = sqrtf(rg.v[p0 + i].x) / bc2_sqrt + k.adam_epsf, dy = sqrtf(rg.v[p0 + i].y) / bc2_sqrt + k.adam_epsf; \
-                const float xx = I[i].x + (neg_step * rg.m[p0 + i].x) / dx, xy = I[i].y + (neg_step * rg.m[p0 + i].y) / dy; \
+                const float dx = sqrtf(v_[i].x) / bc2_sqrt + k.adam_epsf, dy = sqrtf(v_[i].y) / bc2_sqrt + k.adam_epsf; \
+                const float xx = I[i].x + (neg_step * m_[i].x) / dx, xy = I[i].y + (neg_step * m_[i].y) / dy; \
                 rg.I[p0 + i] = fm::f2(xx < k.clampf ? k.clampf : xx, xy < k.clampf ? k.clampf : xy); \
             } \
         }
@@ -548,9 +790,10 @@ OPS_HD float sum_rows(const SumAcc &a) { return ((a.r01.x + a.r01.y) + a.r23.x) 
 // c = M^2 and h = V^2 zero or >= 2^-100.  The fast square root of Adam's v needs v >= 2^-101; v is an EMA of g^2, so
 // anything smaller means g vanished on every epoch so far -- tested per batch, with the generic operators as the
 // (cold) alternative.
-template <int EPL, int NC, int NBX = NBP>
+template <int EPL, int NC, int NBX = NBP, class HM = HomeShared>
 OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs,
-                      const Pass1Consts &pc, double invLe, int l, int case_id, float neg_step, float bc2_sqrt, bool stage_I)
+                      const Pass1Consts &pc, double invLe, int l, int case_id, float neg_step, float bc2_sqrt, bool stage_I,
+                      const HM &hm = HM())
 {
     using fm::F2; using fm::splat; using fm::neg2; using fm::mul2; using fm::add2; using fm::fma2;
     constexpr int NB = NBX;                     // pairs per batch of this instance
@@ -570,6 +813,7 @@ OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneS
     for (int p0 = 0; p0 < NP; p0 += NB) {
         F2 I[NB], c[NB], h[NB], nb[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], d[NB], db[NB], q[NB], qg[NB], g[NB];
         F2 t0[NB], t1[NB], t2[NB];
+        F2 m_[NB], v_[NB];
         Pair mq[2 * NB];
         double ke[2 * NB];
         OPS_P I[i] = rg.I[p0 + i];
@@ -578,9 +822,10 @@ OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneS
             double Mc[2 * NB], Qv[2 * NB];
 #pragma unroll
             for (int s_ = 0; s_ < 2 * NB; ++s_) { Mc[s_] = 0.0; Qv[s_] = 0.0; }      // (the padding half of an odd EPL)
+            if constexpr (HM::TM) hm.template fetch_mq<EPL, 2 * NB>(ls, 2 * p0, mq);
             OPS_S {
                 lo[s_] = table_row(gs.tab, row_offset(rg.spans, 2 * p0 + s_));
-                mq[s_] = ls.mq[(long)(2 * p0 + s_) * ls.ls];
+                if constexpr (!HM::TM) mq[s_] = ls.mq[(long)(2 * p0 + s_) * ls.ls];
                 ke[s_] = slot_ke<EPL>(rg, 2 * p0 + s_);
             }
             OPS_S { Mc[s_] = mq[s_].x + lo[s_].x; Qv[s_] = fma(lo[s_].y, invLe, mq[s_].y); }
@@ -613,7 +858,9 @@ OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneS
         if (stage_I) {
             OPS_P *reinterpret_cast<F2 *>(ls.scr + (long)(p0 + i) * ls.ls) = I[i];
         }
+        hm.template fetch_mv<EPL, NB>(rg, p0, m_, v_);
         OPS_ADAM_STEP
+        hm.template put_mv<EPL, NB>(rg, p0, m_, v_);
         // flexibility sums of the next epoch
         {
             double Id[2 * NB], r[2 * NB], e[2 * NB];
@@ -738,7 +985,12 @@ OPS_HD void team_owner_update(const BeamConsts &k, LaneRegs<EPL> &rg, const Lane
         }
     }
     OPS_FP32_CHAIN
-    { OPS_ADAM_STEP }
+    {
+        F2 m_[NB], v_[NB];
+        OPS_P { m_[i] = rg.m[i]; v_[i] = rg.v[i]; }
+        { OPS_ADAM_STEP }
+        OPS_P { rg.m[i] = m_[i]; rg.v[i] = v_[i]; }
+    }
     OPS_P {
         const int j = case_id + i * NC;
         if (j < NP) {
@@ -804,18 +1056,25 @@ OPS_HD float group_loss(const BeamConsts &k, int n, const LaneStore &ls, int l)
 // once per beam: the record (SingleCore:221-249).  M, V, u, theta belong to the LAST ANALYSED
 // inertias, i.e. the ones the beam's last pass started from (parked by it, stage_I); rg.I holds the stepped ones.
 // ---------------------------------------------------------------------------------------------
-template <int EPL>
+template <int EPL, class HM = HomeShared>
 OPS_HD void lane_emit_forces(int n, const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe, int l,
-                             bool fields, float *shear, float *moment)
+                             bool fields, float *shear, float *moment, const HM &hm = HM(), bool active = true)
 {
+    constexpr int SB = HM::TM ? 4 : 1;          // slots per fetch (HomeTm: the whole warp calls, `active` lanes write)
 #pragma unroll
-    for (int kk = 0; kk < EPL; ++kk) {
-        const int e = LPB * kk + l;
-        if (e < n) {
-            double Mc = 0.0, Qv = 0.0;
-            if (fields) element_forces<EPL>(rg, ls, gs, invLe, kk, Mc, Qv);
-            shear[e] = fields ? (float)Qv : 0.0f;
-            moment[e] = fields ? (float)(-Mc) : 0.0f;
+    for (int k0 = 0; k0 < EPL; k0 += SB) {
+        Pair mq[SB];
+        hm.template fetch_mq<EPL, SB>(ls, k0, mq);
+#pragma unroll
+        for (int s_ = 0; s_ < SB; ++s_) {
+            const int kk = k0 + s_;
+            const int e = LPB * kk + l;
+            if (kk < EPL && e < n && active) {
+                double Mc = 0.0, Qv = 0.0;
+                if (fields) element_forces_mq<EPL>(rg, gs, invLe, kk, mq[s_], Mc, Qv);
+                shear[e] = fields ? (float)Qv : 0.0f;
+                moment[e] = fields ? (float)(-Mc) : 0.0f;
+            }
         }
     }
 }

@@ -361,6 +361,163 @@ extern "C" int hostsim_copy_record(int n, int nn, int64_t row, int64_t rowc, int
     return 0;
 }
 
+// Tensor-memory instance (beamopt_lanes_tm.cu): ONE WARP of the kernel -- four groups taking beams from a counter --
+// with the kernel's loop body: every phase that touches tensor memory (HomeTm; here a plain array of words per lane) is
+// entered by all 32 lanes on a warp-uniform condition, the lanes without work compute on whatever they hold.
+template <int EPL>
+static int lanes_run_tm(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, const int32_t *force_nodes,
+                        const double *force_vals, const double *L, const float *sched, float *I_values,
+                        double *defl, double *rot, float *shear, float *moment, int32_t *epochs, float *loss,
+                        int32_t *status, int nbp)
+{
+    using namespace ops::lanes;
+    const int n = k.n, nn = k.nn;
+    constexpr int NG = 4, TL = NG * LPB, COLS = HomeTm::columns(EPL);
+    std::vector<double> lane_s((size_t)SCR_SLOTS * TL), grp_d((size_t)GROUP_DOUBLES * NG);
+    std::vector<Pair> tab_p((size_t)TAB_SLOTS / 2 * NG);
+    std::vector<int> grp_i((size_t)GROUP_INTS * NG);
+    std::vector<unsigned int> words((size_t)COLS * TL, 0xdeadbeefu);
+    LaneStore ls[NG][LPB];
+    GroupStore gs[NG];
+    HomeTm hm[NG][LPB];
+    static LaneRegs<EPL> rg[NG][LPB];
+    for (int g = 0; g < NG; ++g) {
+        for (int l = 0; l < LPB; ++l) {
+            const int col = g * LPB + l;
+            ls[g][l].ls = TL; ls[g][l].mq = nullptr; ls[g][l].scr = lane_s.data() + col; ls[g][l].xc = nullptr; ls[g][l].xb = nullptr;
+            hm[g][l].base = 0; hm[g][l].w = words.data() + (size_t)COLS * col;
+            lane_reset<EPL>(k, rg[g][l]);
+        }
+        gs[g].gs = NG;
+        gs[g].tab = reinterpret_cast<double *>(tab_p.data()) + (size_t)TAB_SLOTS * g;
+        gs[g].fs.sd = grp_d.data() + g; gs[g].fs.stride = NG;
+        gs[g].gd = gs[g].fs.sd + (size_t)FlexStore::NUM_DOUBLES * NG;
+        gs[g].fs.si = grp_i.data() + g;
+        gs[g].gi = gs[g].fs.si + (size_t)FlexStore::NUM_INTS * NG;
+    }
+    struct GroupState {
+        FlexBeam fb; Pass1Consts pc; int64_t b; bool have, exhausted, resume, fresh; int t, counter, bad; double best; float lossf;
+    } st[NG];
+    for (int g = 0; g < NG; ++g) {
+        memset(&st[g], 0, sizeof st[g]);
+        st[g].b = -1; st[g].best = INFINITY; st[g].lossf = NAN;
+    }
+    int64_t next = 0;
+    while (true) {
+        bool any_have = false, any_fresh = false, any_sums = false;
+        for (int g = 0; g < NG; ++g) {
+            GroupState &s = st[g];
+            s.fresh = false;
+            if (!s.have && !s.exhausted) {
+                const int64_t nb = next++;
+                if (nb < B) {
+                    s.b = nb; s.have = true; s.t = 0; s.counter = 0; s.best = INFINITY; s.lossf = NAN;
+                    int fnode[FLEX_MAXF];
+                    double fval[FLEX_MAXF];
+                    for (int j = 0; j < k.max_forces; ++j) { fnode[j] = force_nodes[nb * k.max_forces + j]; fval[j] = force_vals[nb * k.max_forces + j]; }
+                    const uint8_t *fx = fixed_uy + nb * nn;
+                    FlexBeam f0;
+                    const int rc = flex_setup(k, L[nb], [&](int i) { return fx[i] != 0; }, k.max_forces, fnode, fval, gs[g].fs, f0);
+                    group_publish(f0, rc, gs[g]);
+                    group_table_init(gs[g]);
+                    s.bad = group_fetch(k, L[nb], gs[g], s.fb);
+                    s.pc = pass1_consts(s.fb);
+                    for (int l = 0; l < LPB; ++l) {
+                        if (!s.bad) lane_init<EPL, HomeTm>(k, n, s.fb, gs[g], ls[g][l], l, rg[g][l], hm[g][l]);
+                        else lane_reset<EPL>(k, rg[g][l]);
+                    }
+                    s.fresh = !s.bad;
+                } else s.exhausted = true;
+            }
+            any_have = any_have || s.have; any_fresh = any_fresh || s.fresh; any_sums = any_sums || s.fresh || s.resume;
+        }
+        if (!any_have) break;
+        if (any_fresh)
+            for (int g = 0; g < NG; ++g) for (int l = 0; l < LPB; ++l) tm_commit<EPL>(hm[g][l], ls[g][l], st[g].fresh);
+        if (any_sums)
+            for (int g = 0; g < NG; ++g) for (int l = 0; l < LPB; ++l)
+                lane_pass1<EPL, HomeTm>(rg[g][l], ls[g][l], st[g].pc, st[g].resume, hm[g][l], st[g].fresh || st[g].resume);
+        bool run[NG], done[NG], stage_I[NG], any_run = false, any_rec = false;
+        int rc[NG];
+        for (int g = 0; g < NG; ++g) {
+            GroupState &s = st[g];
+            s.resume = false;
+            run[g] = s.have && k.max_epochs > 0 && s.bad == 0;
+            done[g] = s.have && !run[g];
+            rc[g] = 0;
+            any_run = any_run || run[g];
+            if (run[g]) {
+                for (int l = 0; l < LPB; ++l) lane_reduce(l, s.fb.m, ls[g][l], gs[g]);
+                for (int l = LPB - 1; l >= 0; --l) rc[g] |= group_solve(s.fb, gs[g], l);
+            }
+            stage_I[g] = run[g] && ((s.t + 1 >= k.max_epochs) || (k.early_stop && s.counter + 1 >= k.patience));
+        }
+        if (any_run) {
+            for (int g = 0; g < NG; ++g) {
+                GroupState &s = st[g];
+                const float neg_step = run[g] ? sched[2 * s.t] : 0.0f, bc2_sqrt = run[g] ? sched[2 * s.t + 1] : 1.0f;
+                for (int l = 0; l < LPB; ++l) {
+                    if (nbp == 1) lane_pass<EPL, 1, 1, HomeTm>(k, n, rg[g][l], ls[g][l], gs[g], s.pc, s.fb.invLe, l, 0, neg_step, bc2_sqrt, stage_I[g], hm[g][l]);
+                    else if (nbp == 3) lane_pass<EPL, 1, 3, HomeTm>(k, n, rg[g][l], ls[g][l], gs[g], s.pc, s.fb.invLe, l, 0, neg_step, bc2_sqrt, stage_I[g], hm[g][l]);
+                    else lane_pass<EPL, 1, 2, HomeTm>(k, n, rg[g][l], ls[g][l], gs[g], s.pc, s.fb.invLe, l, 0, neg_step, bc2_sqrt, stage_I[g], hm[g][l]);
+                    if (s.have && !run[g]) lane_reset<EPL>(k, rg[g][l]);
+                }
+            }
+        }
+        for (int g = 0; g < NG; ++g) {
+            GroupState &s = st[g];
+            if (run[g]) {
+                float lv[LPB];
+                for (int l = 0; l < LPB; ++l) lv[l] = group_loss(k, n, ls[g][l], l);
+                for (int l = 1; l < LPB; ++l) if (memcmp(&lv[l], &lv[0], 4) != 0) return -100;
+                s.lossf = lv[0];
+                ++s.t;
+                if (rc[g] || !(s.lossf - s.lossf == 0.0f)) { s.bad = 1; done[g] = true; }
+                if (k.early_stop) {
+                    const double l_ = (double)s.lossf;
+                    if (l_ < s.best - k.tol) { s.best = l_; s.counter = 0; } else { ++s.counter; }
+                    if (s.counter >= k.patience) done[g] = true;
+                }
+                if (s.t >= k.max_epochs) done[g] = true;
+            }
+            any_rec = any_rec || (s.have && done[g]);
+        }
+        for (int g = 0; g < NG; ++g) {
+            GroupState &s = st[g];
+            const bool rec = s.have && done[g];
+            const bool fields = (s.t > 0) && (s.bad == 0);
+            const int64_t row = s.b < 0 ? 0 : s.b;
+            if (any_rec)
+                for (int l = 0; l < LPB; ++l)
+                    lane_emit_forces<EPL, HomeTm>(n, rg[g][l], ls[g][l], gs[g], s.fb.invLe, l, fields, shear + row * n, moment + row * n,
+                                                  hm[g][l], rec);
+            if (rec) {
+                const ParkedInertia parked = {reinterpret_cast<const float *>(ls[g][0].scr), ls[g][0].ls};
+                group_emit_displacements(k, s.fb, gs[g], fields, parked, defl + row * nn, rot + row * nn);
+                for (int l = 0; l < LPB; ++l) lane_emit_inertias<EPL>(n, rg[g][l], l, I_values + row * n);
+                epochs[row] = s.t; loss[row] = s.lossf; status[row] = s.bad;
+                s.have = false;
+            } else if (stage_I[g]) {
+                s.resume = true;
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int hostsim_beamopt_lanes_tm(const OpsBeamOptParams *p, int nbp, int64_t B, const uint8_t *fixed_uy,
+                                        const int32_t *force_nodes, const double *force_vals, const double *L,
+                                        const float *sched, float *I_values, double *defl, double *rot,
+                                        float *shear, float *moment, int32_t *epochs, float *loss, int32_t *status)
+{
+    if (p->max_forces > FLEX_MAXF || p->num_cases != 1) return OPS_E_UNSUPP;
+    BeamConsts k;
+    consts_from(p, &k);
+    if (k.n <= 64 || k.n > 104) return OPS_E_UNSUPP;
+    return lanes_run_tm<13>(k, B, fixed_uy, force_nodes, force_vals, L, sched, I_values, defl, rot, shear, moment, epochs,
+                            loss, status, nbp);
+}
+
 extern "C" int hostsim_beamopt_lanes(const OpsBeamOptParams *p, int64_t B, const uint8_t *fixed_uy,
                                      const int32_t *force_nodes, const double *force_vals, const double *L,
                                      const float *sched, float *I_values, double *defl, double *rot,

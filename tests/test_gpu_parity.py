@@ -321,6 +321,31 @@ def test_many_round_batches_use_the_larger_cta_and_agree_bitwise(monkeypatch):
     assert_matches_oracle(o, {k: v[sl] for k, v in a.items()})
 
 
+@pytest.mark.parametrize("script,flag,early_stop,B", [("MC", 0, False, 148 * 64), ("MC", 0, True, 3000), ("SC", 1, True, 2000)])
+def test_tensor_memory_instance_agrees_bitwise(monkeypatch, script, flag, early_stop, B):
+    """beamopt_lanes_tm.cu keeps {M0, Q0}, m, v of a lane in tensor memory (tcgen05.ld / tcgen05.st) and holds 64 beams
+    per SM; the planner picks it for single rounds of 52..64 beams per SM with a fixed epoch count.  Same phase
+    functions, so the record equals the register / shared-memory instance's bit for bit: a full single round, ragged
+    early stopping (fresh beams committed next to running ones), random bridges with rejected beams in between."""
+    p = BeamOptParams.for_script(script).replace(early_stop=early_stop)
+    if not early_stop:
+        p = p.replace(max_e=200)
+    cases = seeded_cases(p, B, seed=77, flag=flag)
+    cases[5] = (200.0, [], [50], [-1e5])                                  # mechanism
+    cases[41] = (200.0, [10, 20, 30, 40, 50, 60], [55], [-1e5])          # more rollers than the three-moment kernels take
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    monkeypatch.setenv("OPS_LANES_TM", "0")
+    a = gpu_run(p, fixed, fn, fv, L)
+    monkeypatch.setenv("OPS_LANES_TM", "1")
+    b = gpu_run(p, fixed, fn, fv, L)
+    monkeypatch.delenv("OPS_LANES_TM", raising=False)
+    c = gpu_run(p, fixed, fn, fv, L)                                      # the planner's own choice
+    assert a["status"][5] == 1 and a["status"][41] == 3 and (a["status"] == 0).sum() == B - 2
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+        assert np.array_equal(a[k], c[k], equal_nan=True), k
+
+
 def test_generate_samples_batched_is_a_drop_in():
     """Same entry point, arguments and record schema as the reference's generate_sample."""
     rollers, avail = sampling.fixed_bridge(101)

@@ -241,3 +241,30 @@ def test_batch_size_of_the_stage_major_batches_does_not_change_the_bits(tmp_path
             for k in want:
                 assert np.array_equal(want[k], got[k]), (nb, num_cases, k)
     assert helpers._hs is base
+
+
+@pytest.mark.parametrize("nbp", [1, 2, 3])
+@pytest.mark.parametrize("script,flag,early,max_e,count", [("MC", 0, True, None, 61), ("SC", 1, True, None, 45),
+                                                           ("MC", 0, False, 150, 22), ("SC", 0, True, 0, 12)])
+def test_tensor_memory_instance_equals_the_register_instance(script, flag, early, max_e, count, nbp):
+    """beamopt_lanes_tm.cu keeps {M0, Q0}, m, v of a lane in tensor memory and enters every phase that touches it with
+    the whole warp, idle groups included.  The host model runs ONE WARP of that kernel -- four groups pulling beams from
+    a counter, stopping at different epochs, a plain word array per lane as the tensor memory -- and must reproduce the
+    register / shared-memory instance bit for bit: ragged early stopping (fresh beams next to running ones: the
+    read-modify-write commit), parked epochs that go on, rejected beams (mechanism, > 5 rollers) next to running ones,
+    zero epochs, any batch size of the pass."""
+    p = BeamOptParams.for_script(script).replace(early_stop=early)
+    if max_e is not None:
+        p = p.replace(max_e=max_e)
+    cases = seeded_cases(p, count, seed=23, flag=flag)
+    # rejected beams in between: a mechanism (no roller) and an unsupported support count
+    cases.insert(3, (200.0, [], [50], [-1e5]))
+    cases.insert(9, (200.0, [10, 20, 30, 40, 50, 60], [55], [-1e5]))
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases)
+    want = hostsim_run(p, fixed, fn, fv, L, solver=0)
+    got = hostsim_run(p, fixed, fn, fv, L, solver="tm", tm_nbp=nbp)
+    assert want["status"][3] == 1 and want["status"][9] == 3
+    if early and max_e is None:
+        assert len(set(want["epochs"].tolist())) > 10          # the groups really stop at different epochs
+    for key in want:
+        assert np.array_equal(want[key], got[key], equal_nan=True), key
