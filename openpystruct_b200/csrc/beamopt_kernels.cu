@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/openpystruct_b200.h"
 #include "beamopt_core.cuh"
 #include "beamopt_flex.cuh"
@@ -699,6 +701,117 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
                        moment, epochs, loss, status, 0, nullptr, 0, d_workspace, workspace_bytes, cuda_stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dataset gather with a FIXED epoch count: all beams of a round finish in the same epoch, so the in-kernel copy of a
+// round's records to the peers (lane_copy_record) is a burst at the end of the round that no iteration is left to hide
+// (8 GPUs: 0.85 ms of a 5.6 ms step, profiles/r02_scatter_ab_n8.txt).  Such batches run as a PIPELINE instead: the
+// plain kernel instance, launched in chunks of whole rounds into this GPU's arrays, and after every chunk a copy kernel
+// on a side stream that stores the chunk's rows -- contiguous blocks of the eight arrays -- into the peers' arrays over
+// NVLink while the next chunk iterates (it fits beside the compute CTA: no shared memory, 128 threads).  Only the last
+// chunk's copy is exposed.  Early-stopped batches keep the in-kernel copy: there the beams end at different epochs and
+// the copies hide behind the other groups' iterations.
+// ---------------------------------------------------------------------------------------------
+#define OPS_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+struct PeerCopyJob {
+    int nd, arrays;
+    char *base[lanes::MAX_DEST][8];             // [destination][array]
+    long long first[8], bytes[8];               // byte range of the chunk's rows inside each array
+};
+
+struct alignas(16) CopyUnit16 { unsigned long long a, b; };
+
+// every 16-byte unit is read once and stored to all peers; ragged 4-byte heads / tails of a range (rows are multiples
+// of 4 bytes, the array bases 256-byte aligned) go one word at a time
+__global__ void __launch_bounds__(128) peer_copy_kernel(const PeerCopyJob job)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    for (int a = 0; a < job.arrays; ++a) {
+        const long long lo = job.first[a], hi = lo + job.bytes[a];
+        long long body_lo = (lo + 15) & ~15LL, body_hi = hi & ~15LL;
+        if (body_lo > body_hi) { body_lo = hi; body_hi = hi; }
+        const char *src = job.base[0][a];
+        for (long long u = tid; u < ((body_hi - body_lo) >> 4); u += nthreads) {
+            const CopyUnit16 v = *reinterpret_cast<const CopyUnit16 *>(src + body_lo + (u << 4));
+            for (int r = 1; r < job.nd; ++r) *reinterpret_cast<CopyUnit16 *>(job.base[r][a] + body_lo + (u << 4)) = v;
+        }
+        const long long head = (body_lo - lo) >> 2, tail = (hi - body_hi) >> 2;
+        for (long long u = tid; u < head + tail; u += nthreads) {
+            const long long off = u < head ? lo + (u << 2) : body_hi + ((u - head) << 2);
+            const unsigned int v = *reinterpret_cast<const unsigned int *>(src + off);
+            for (int r = 1; r < job.nd; ++r) *reinterpret_cast<unsigned int *>(job.base[r][a] + off) = v;
+        }
+    }
+}
+
+// side stream + fork / join events of the pipeline, one set per device, created on first use
+struct ScatterPipe {
+    cudaStream_t side;
+    cudaEvent_t fork, join;
+    bool ready;
+};
+static ScatterPipe g_pipe[64];
+static std::mutex g_pipe_mutex;
+
+static int scatter_pipe(ScatterPipe **out)
+{
+    int dev = 0;
+    OPS_CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return OPS_E_BADARG;
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    ScatterPipe &sp = g_pipe[dev];
+    if (!sp.ready) {
+        OPS_CU(cudaStreamCreateWithFlags(&sp.side, cudaStreamNonBlocking));
+        OPS_CU(cudaEventCreateWithFlags(&sp.fork, cudaEventDisableTiming));
+        OPS_CU(cudaEventCreateWithFlags(&sp.join, cudaEventDisableTiming));
+        sp.ready = true;
+    }
+    *out = &sp;
+    return 0;
+}
+
+static int launch_scatter_pipelined(const OpsBeamOptParams *p, int64_t B, int64_t chunk,
+                                    const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
+                                    const double *L, const float *d_schedule, int n_dest,
+                                    const OpsBeamOptRecordArrays *dests, int64_t row0, void *d_workspace,
+                                    size_t workspace_bytes, cudaStream_t stream)
+{
+    ScatterPipe *sp = nullptr;
+    int rc = scatter_pipe(&sp);
+    if (rc) return rc;
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const size_t nn = (size_t)p->num_nodes, n = nn - 1, C = (size_t)p->num_cases, F = (size_t)p->max_forces * C;
+    const size_t row_bytes[8] = {n * 4, C * nn * 8, C * nn * 8, C * n * 4, C * n * 4, 4, 4, 4};
+    for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+        const int64_t m = (B - r0) < chunk ? (B - r0) : chunk;
+        rc = launch_impl(p, m, fixed_uy + (size_t)r0 * nn, force_nodes ? force_nodes + (size_t)r0 * F : nullptr,
+                         force_vals ? force_vals + (size_t)r0 * F : nullptr, L + r0, d_schedule, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, nullptr, nullptr, nullptr, 1, dests, row0 + r0, d_workspace, workspace_bytes,
+                         (void *)stream);
+        if (rc) return rc;
+        PeerCopyJob job;
+        memset(&job, 0, sizeof job);
+        job.nd = n_dest; job.arrays = 8;
+        for (int r = 0; r < n_dest; ++r) {
+            const OpsBeamOptRecordArrays &a = dests[r];
+            char *b8[8] = {(char *)a.I_values, (char *)a.deflections, (char *)a.rotations, (char *)a.shear, (char *)a.moment,
+                           (char *)a.epochs, (char *)a.loss, (char *)a.status};
+            for (int i = 0; i < 8; ++i) { if (!b8[i]) return OPS_E_BADARG; job.base[r][i] = b8[i]; }
+        }
+        for (int i = 0; i < 8; ++i) {
+            job.first[i] = (long long)((size_t)(row0 + r0) * row_bytes[i]);
+            job.bytes[i] = (long long)((size_t)m * row_bytes[i]);
+        }
+        OPS_CU(cudaEventRecord(sp->fork, stream));
+        OPS_CU(cudaStreamWaitEvent(sp->side, sp->fork, 0));
+        peer_copy_kernel<<<sms * 4, 128, 0, sp->side>>>(job);
+        OPS_CU(cudaGetLastError());
+    }
+    OPS_CU(cudaEventRecord(sp->join, sp->side));
+    OPS_CU(cudaStreamWaitEvent(stream, sp->join, 0));
+    return 0;
+}
+
 int ops_beamopt_launch_scatter(const OpsBeamOptParams *p, int64_t B,
                                const uint8_t *fixed_uy, const int32_t *force_nodes, const double *force_vals,
                                const double *L, const float *d_schedule,
@@ -706,6 +819,24 @@ int ops_beamopt_launch_scatter(const OpsBeamOptParams *p, int64_t B,
                                void *d_workspace, size_t workspace_bytes, void *cuda_stream)
 {
     if (n_dest < 1) return OPS_E_BADARG;
+    // fixed epoch count and more than one peer: chunks of whole rounds + the copy kernel.  With a single peer the copy
+    // inside the kernel is as good as free (2 GPUs: 4.83 ms against 4.81 ms on one), with seven it is 0.85 ms of the step.
+    // OPS_SCATTER_IN_KERNEL / OPS_SCATTER_PIPELINED force either form (A/B runs; same results).
+    const bool pipelined = getenv("OPS_SCATTER_PIPELINED") ? true : (getenv("OPS_SCATTER_IN_KERNEL") ? false : n_dest > 2);
+    if (n_dest > 1 && n_dest <= lanes::MAX_DEST && dests && B > 0 && p && !p->early_stop && pipelined) {
+        BeamConsts k;
+        int rc = make_consts(p, &k);
+        if (rc) return rc;
+        LaunchPlan pl;
+        rc = plan_launch(k, p->num_cases, B, p->solver, &pl);
+        if (rc) return rc;
+        if (!(pl.lanes && lanes_scatter_supported(pl.lp))) return OPS_E_UNSUPP;
+        int64_t chunk = (int64_t)pl.lp.blocks * (pl.lp.threads / (lanes::LPB * p->num_cases));
+        if (!pl.lp.tm && pl.lp.threads > 320) chunk *= 3;            // the 384-thread instance is chosen for >= 3 rounds
+        if (chunk <= 0 || B < chunk + chunk / 4) chunk = B;
+        return launch_scatter_pipelined(p, B, chunk, fixed_uy, force_nodes, force_vals, L, d_schedule, n_dest, dests, row0,
+                                        d_workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+    }
     return launch_impl(p, B, fixed_uy, force_nodes, force_vals, L, d_schedule, nullptr, nullptr, nullptr, nullptr,
                        nullptr, nullptr, nullptr, nullptr, n_dest, dests, row0, d_workspace, workspace_bytes, cuda_stream);
 }

@@ -129,9 +129,17 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     // beams in order from a counter in shared memory.  Every SM gets the same number of beams (+-1), so
     // the last, partially filled round runs with few groups on EVERY SM (short iterations) instead of
     // full on some SMs and empty on others; ragged stopping is still absorbed inside the CTA.
+    // Which group takes which beam.  The FIRST beam of a group is static (group g / team g takes the CTA's g-th beam),
+    // the others come from a counter that starts behind that first round.  A launch that does not fill every group --
+    // the last chunk of a pipelined run, a small batch -- then runs on the LOWEST warps, i.e. evenly spread over the four
+    // schedulers; a race for the counter hands the beams to whichever warps arrive first, often several of one
+    // scheduler, and the partial round takes as long as a full one (16 beams per SM: 4.4 us per epoch against 3.0 us,
+    // 27.6: 4.5 against 3.7; profiles/r02_static_first_round.txt).  Later rounds of the same launch stay on the counter:
+    // measured faster than a static order there (10 000 beams: 4.78 ms against 4.87 ms).
     __shared__ unsigned int cta_next;
-    if (tid == 0) cta_next = 0;
+    if (tid == 0) cta_next = (unsigned int)(G / NC);
     __syncthreads();
+    unsigned int my_next = (unsigned int)(g / NC);                 // CTA-local index of the group's next static beam
 #ifdef OPS_LANES_STAGGER_NS
     // A/B knob: warps start their first epoch OPS_LANES_STAGGER_NS apart (per scheduler slot w / 4, plus a quarter of
     // that per scheduler), so that the resident warps are not all in the same phase of the epoch at the same time
@@ -154,7 +162,11 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     while (true) {
         if (!have && !exhausted) {
             long long nb = 0;
-            if (NC == 1) {
+            const bool fixed_turn = b < 0;                         // the group's first beam
+            if (fixed_turn) {
+                nb = (long long)blockIdx.x + (long long)gridDim.x * my_next;
+                my_next += (unsigned int)(G / NC);
+            } else if (NC == 1) {
                 if (l == 0) nb = (long long)blockIdx.x + (long long)gridDim.x * atomicAdd(&cta_next, 1u);
                 nb = __shfl_sync(gmask, nb, 0, LPB);
             } else {

@@ -97,7 +97,7 @@ beamopt_lanes_tm_kernel(const BeamConsts k, const long long B, const OptPtrs p)
                      ::"r"((unsigned int)__cvta_generic_to_shared(&tm_base)), "n"(TM_COLUMNS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) cta_next = 0;
+    if (tid == 0) cta_next = (unsigned int)G;                       // (static first round, beamopt_lanes.cu)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -110,6 +110,7 @@ beamopt_lanes_tm_kernel(const BeamConsts k, const long long B, const OptPtrs p)
     memset(&fb, 0, sizeof fb);
     Pass1Consts pc = {0.0, 0.0, 0.0, 0.0};
     long long b = -1;
+    unsigned int my_next = (unsigned int)g;
     bool have = false, exhausted = false, resume = false;
     int t = 0, counter = 0, bad = 0;
     double best = INFINITY;
@@ -119,8 +120,13 @@ beamopt_lanes_tm_kernel(const BeamConsts k, const long long B, const OptPtrs p)
         bool fresh = false;
         if (!have && !exhausted) {
             long long nb = 0;
-            if (l == 0) nb = (long long)blockIdx.x + (long long)gridDim.x * atomicAdd(&cta_next, 1u);
-            nb = __shfl_sync(gmask, nb, 0, LPB);
+            if (b < 0) {                                            // static first turn (beamopt_lanes.cu)
+                nb = (long long)blockIdx.x + (long long)gridDim.x * my_next;
+                my_next += (unsigned int)G;
+            } else {
+                if (l == 0) nb = (long long)blockIdx.x + (long long)gridDim.x * atomicAdd(&cta_next, 1u);
+                nb = __shfl_sync(gmask, nb, 0, LPB);
+            }
             if (nb < B) {
                 b = nb;
                 have = true;

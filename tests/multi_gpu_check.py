@@ -24,10 +24,16 @@ from tests.helpers import seeded_cases                                   # noqa:
 def main():
     rank, local, world = init_from_env("nccl")
     dev = torch.device("cuda", local)
-    for script, count, cases_per_beam in (("MC", 3001, 1), ("SC", 777, 1), ("MC", 402, 4)):
+    # early-stopped batches: the record copy inside the kernel; fixed epoch counts (max_e given): chunks of whole rounds +
+    # the peer-copy kernel on a side stream -- one chunk, several chunks with a ragged last one, four load cases
+    for script, count, cases_per_beam, max_e in (("MC", 3001, 1, None), ("SC", 777, 1, None), ("MC", 402, 4, None),
+                                                 ("MC", 1203, 1, 40), ("MC", 148 * 40 * world * 2 + 333, 1, 6),
+                                                 ("MC", 395, 4, 25)):
         p = BeamOptParams.for_script(script)
         if cases_per_beam > 1:
             p = p.replace(num_cases=cases_per_beam)
+        if max_e is not None:
+            p = p.replace(early_stop=False, max_e=max_e)
         cases = seeded_cases(p, count * cases_per_beam, seed=17)
         fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases, cases_per_beam)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
@@ -45,6 +51,7 @@ def main():
         ds.close()
         if rank == 0:
             print(f"multi_gpu_check ok: {script} x{cases_per_beam} {count} beams on {world} GPUs, "
+                  f"{'early stop' if max_e is None else 'fixed epochs (pipelined peer copy)'}, "
                   f"epochs {int(want['epochs'].min())}..{int(want['epochs'].max())}", flush=True)
     # the host-level entry under torchrun: every rank draws the same seeded cases, the beams are sharded, every rank
     # gets the whole dataset -- equal to the single-GPU run of all beams on this rank
