@@ -39,6 +39,7 @@
 
 #include "beamopt_flex.cuh"
 #include "fastmath.cuh"
+#include "beamopt_lanes.cuh"      // the packed fp32 chain (OPS_FP32_CHAIN, OPS_ADAM_STEP): one source for both kernel families
 
 namespace ops {
 namespace wide {
@@ -339,6 +340,38 @@ OPS_HD void adam_batch(const BeamConsts &k, float neg_step, float bc2_sqrt, floa
 }
 #undef OPS_W
 
+// The same two halves on PAIRS of slots (2 j, 2 j + 1) with sm_100a's packed fp32 instructions -- the stage-major chain of
+// beamopt_lanes.cuh itself (FFMA2 / FMUL2 / FADD2, each half rounded like the scalar instruction; un-fused product-then-
+// sum sites written with scalar adds, scripts/sass_packed_audit.py).  Used for batches of an even slot count.
+template <int NPB>
+OPS_HD void loss_grad_pairs(const BeamConsts &k, const fm::F2 (&I)[NPB], const fm::F2 (&c)[NPB], const fm::F2 (&h)[NPB],
+                            fm::F2 (&d)[NPB], fm::F2 (&q)[NPB], fm::F2 (&g)[NPB])
+{
+    using fm::F2; using fm::splat; using fm::neg2; using fm::mul2; using fm::add2; using fm::fma2;
+    constexpr int NB = NPB;
+    const F2 one = splat(1.0f), half = splat(0.5f);
+    F2 nb[NB], y[NB], rb[NB], s[NB], gg[NB], rgg[NB], rs[NB], db[NB], qg[NB], t0[NB], t1[NB], t2[NB];
+#define OPS_P _Pragma("unroll") for (int i = 0; i < NB; ++i)
+    OPS_FP32_CHAIN
+#undef OPS_P
+}
+
+template <int NPB>
+OPS_HD void adam_pairs(const BeamConsts &k, float neg_step, float bc2_sqrt, float rbc, fm::F2 (&I)[NPB], fm::F2 (&m_)[NPB],
+                       fm::F2 (&v_)[NPB], const fm::F2 (&g)[NPB])
+{
+    using fm::F2; using fm::splat; using fm::neg2; using fm::mul2; using fm::add2; using fm::fma2;
+    constexpr int NB = NPB, p0 = 0;
+    const F2 one = splat(1.0f), half = splat(0.5f);
+    F2 y[NB], t0[NB], t1[NB], t2[NB];
+    struct { F2 I[NB]; } rg;
+#define OPS_P _Pragma("unroll") for (int i = 0; i < NB; ++i)
+    OPS_ADAM_STEP
+    OPS_P I[i] = rg.I[p0 + i];
+#undef OPS_P
+    (void)one;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per epoch
 // ---------------------------------------------------------------------------------------------
@@ -425,7 +458,21 @@ OPS_HD void sweep_batch(const BeamConsts &k, const FlexBeam &fb, const WideShape
         for (int i = 0; i < N; ++i) { c[i] = (float)Mc[i]; h[i] = (float)Qv[i]; }
 #pragma unroll
         for (int i = 0; i < N; ++i) { c[i] = c[i] * c[i]; h[i] = h[i] * h[i]; }
-        loss_grad_batch<N>(k, I, c, h, d, q, g);
+        if constexpr (N % 2 == 0) {
+            fm::F2 Ip[N / 2], cp[N / 2], hp[N / 2], dp[N / 2], qp[N / 2], gp[N / 2];
+#pragma unroll
+            for (int j = 0; j < N / 2; ++j) {
+                Ip[j] = fm::f2(I[2 * j], I[2 * j + 1]); cp[j] = fm::f2(c[2 * j], c[2 * j + 1]); hp[j] = fm::f2(h[2 * j], h[2 * j + 1]);
+            }
+            loss_grad_pairs<N / 2>(k, Ip, cp, hp, dp, qp, gp);
+#pragma unroll
+            for (int j = 0; j < N / 2; ++j) {
+                d[2 * j] = dp[j].x; d[2 * j + 1] = dp[j].y; q[2 * j] = qp[j].x; q[2 * j + 1] = qp[j].y;
+                g[2 * j] = gp[j].x; g[2 * j + 1] = gp[j].y;
+            }
+        } else {
+            loss_grad_batch<N>(k, I, c, h, d, q, g);
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int s = kb + i;
@@ -442,7 +489,22 @@ OPS_HD void sweep_batch(const BeamConsts &k, const FlexBeam &fb, const WideShape
                 for (int w = 0; w < 3; ++w) { cx.lv[w] += cx.acc[w][0]; cx.acc[w][0] = 0.0f; }
             }
         }
-        adam_batch<N>(k, sc.neg_step, sc.bc2_sqrt, sc.rbc, I, m, v, g);
+        if constexpr (N % 2 == 0) {
+            fm::F2 Ip[N / 2], mp[N / 2], vp[N / 2], gp[N / 2];
+#pragma unroll
+            for (int j = 0; j < N / 2; ++j) {
+                Ip[j] = fm::f2(I[2 * j], I[2 * j + 1]); mp[j] = fm::f2(m[2 * j], m[2 * j + 1]);
+                vp[j] = fm::f2(v[2 * j], v[2 * j + 1]); gp[j] = fm::f2(g[2 * j], g[2 * j + 1]);
+            }
+            adam_pairs<N / 2>(k, sc.neg_step, sc.bc2_sqrt, sc.rbc, Ip, mp, vp, gp);
+#pragma unroll
+            for (int j = 0; j < N / 2; ++j) {
+                I[2 * j] = Ip[j].x; I[2 * j + 1] = Ip[j].y; m[2 * j] = mp[j].x; m[2 * j + 1] = mp[j].y;
+                v[2 * j] = vp[j].x; v[2 * j + 1] = vp[j].y;
+            }
+        } else {
+            adam_batch<N>(k, sc.neg_step, sc.bc2_sqrt, sc.rbc, I, m, v, g);
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int e = LPB * (kb + i) + l;

@@ -31,9 +31,28 @@ for m in re.finditer(r"Function : (\S*beamopt_lanes_kernelILi(\d+)ELi(\d+)ELi(\d
     # a contraction turns one FMUL2 + one FADD2 into an FFMA2: the FMUL2 count is the proof (ptxas may ADD packed
     # instructions of its own -- two scalar adds of the generic-n sums as one FADD2, a scalar Newton step as an FFMA2 --
     # which changes no rounding)
-    good = n["FMUL2"] == want_mul and n["FADD2"] >= min(want_add, 3 * chain_pairs) and abs(n["FFMA2"] - want_fma) <= 1
+    # An FMUL2 MORE than the source has (ptxas packing two scalar products, or cloning a block) cannot come from a
+    # contraction; it is accepted only together with the exact FFMA2 count.
+    extra_mul = n["FMUL2"] - want_mul
+    good = extra_mul >= 0 and n["FADD2"] >= min(want_add, 3 * chain_pairs) and \
+        (abs(n["FFMA2"] - want_fma) <= 1 if extra_mul == 0 else n["FFMA2"] == want_fma)
     ok &= good
     print(f"{'ok ' if good else 'BAD'} <EPL {epl:2d}, n {nfix:3d}, cases {nc}, T {tfix:3d}, scatter {sc}>  "
+          f"FFMA2 {n['FFMA2']:3d} (want {want_fma})  FMUL2 {n['FMUL2']:3d} (want {want_mul})  FADD2 {n['FADD2']:3d} (want {want_add}{'+' if not nfix else ''})")
+# the tensor-memory instances (beamopt_lanes_tm.cu: <EPL, n, T, scatter>, single case): the same pass
+for m in re.finditer(r"Function : (\S*beamopt_lanes_tm_kernelILi(\d+)ELi(\d+)ELi(\d+)ELb([01])\S*)(.*?)(?=Function :|\Z)", sass, re.S):
+    epl, nfix, tfix, sc, body = int(m.group(2)), int(m.group(3)), int(m.group(4)), m.group(5), m.group(6)
+    pairs = (epl + 1) // 2
+    n = {op: len(re.findall(r"\b%s\b" % op, body)) for op in ("FFMA2", "FMUL2", "FADD2")}
+    n["FFMA2"] -= len(re.findall(r"FFMA2 R\d+, -?U?R\d+(?:\.reuse)?\.F32, -?U?R\d+(?:\.reuse)?\.F32,", body))
+    want_fma, want_mul = 28 * pairs, 25 * pairs
+    blk_pairs = (((nfix // 8) // 4) * 4) // 2 if nfix else 0
+    want_add = 3 * pairs + 3 * blk_pairs
+    extra_mul = n["FMUL2"] - want_mul
+    good = extra_mul >= 0 and n["FADD2"] >= min(want_add, 3 * pairs) and \
+        (abs(n["FFMA2"] - want_fma) <= 1 if extra_mul == 0 else n["FFMA2"] == want_fma)
+    ok &= good
+    print(f"{'ok ' if good else 'BAD'} tensor memory <EPL {epl:2d}, n {nfix:3d}, T {tfix:3d}, scatter {sc}>  "
           f"FFMA2 {n['FFMA2']:3d} (want {want_fma})  FMUL2 {n['FMUL2']:3d} (want {want_mul})  FADD2 {n['FADD2']:3d} (want {want_add}{'+' if not nfix else ''})")
 print("packed audit:", "PASS" if ok else "FAIL")
 sys.exit(0 if ok else 1)
