@@ -137,6 +137,11 @@ int ops_beamopt_launch(const OpsBeamOptParams *p, int64_t B,
  * mapped into this process with ops_peer_open.  Beam b of this launch is written to row row0 + b of set 0 and
  * copied by the same thread group to that row of every other set (stores over NVLink) while the other beams keep
  * iterating, so when all ranks' launches have completed every GPU holds the complete dataset; the caller orders that with a barrier on the stream (e.g. a one-element NCCL all_reduce).
+ * With a FIXED epoch count (early_stop = 0) and more than one peer the call runs as a pipeline instead -- the plain
+ * kernel in chunks of whole rounds, and after every chunk a copy kernel on a library-owned side stream that stores the
+ * chunk's rows into the peers' sets while the next chunk iterates (all beams of a round finish together there, so the
+ * in-kernel copy would be an exposed burst); the side stream is joined back into `cuda_stream` before the call
+ * returns, so the stream-ordering contract is the same.
  * Production (lanes) kernel only: OPS_E_UNSUPP for configurations that run another kernel.
  */
 typedef struct OpsBeamOptRecordArrays {

@@ -19,7 +19,7 @@ bench.select_workload(os.environ.get("SWEEP_WORKLOAD", "cfg2"), 1)
 bench.EPOCHS = epochs
 p = bench.workload_params(early_stop=early)
 dev = torch.device("cuda", 0)
-fixed, fn, fv, L = bench.sample_inputs(max(counts), seed=1000)
+fixed, fn, fv, L = bench.sample_inputs(max(counts), seed=int(os.environ.get("SWEEP_SEED", "1000")))
 d_all = [torch.from_numpy(a).to(dev) for a in (fixed, fn, fv, L)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for B in counts:

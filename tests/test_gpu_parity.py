@@ -346,6 +346,56 @@ def test_tensor_memory_instance_agrees_bitwise(monkeypatch, script, flag, early_
         assert np.array_equal(a[k], c[k], equal_nan=True), k
 
 
+@pytest.mark.parametrize("mode,num_cases,B", [("in_kernel", 1, 700), ("in_kernel", 4, 160), ("pipelined", 1, 148 * 40 * 2 + 333),
+                                              ("pipelined", 1, 901), ("pipelined", 4, 211)])
+def test_dataset_gather_entry_on_one_gpu(monkeypatch, mode, num_cases, B):
+    """ops_beamopt_launch_scatter with THREE destination sets that all live on this GPU (the peers' arrays of a
+    multi-GPU job are just more device pointers): rows row0 .. row0 + B of every set must equal the plain launch's
+    record, every other row must stay untouched.  Both forms of the gather: the copy inside the kernel (early-stopped
+    batches) and the pipeline of chunked launches + peer_copy_kernel on the side stream (fixed epoch counts; several
+    chunks with a ragged last one, an odd row0 so that the 808-byte rows start 8-byte aligned only)."""
+    import ctypes as C
+    p = BeamOptParams.for_script("MC").replace(num_cases=num_cases)
+    if mode == "pipelined":
+        p = p.replace(early_stop=False, max_e=7)
+        monkeypatch.setenv("OPS_SCATTER_PIPELINED", "1")
+    else:
+        monkeypatch.setenv("OPS_SCATTER_IN_KERNEL", "1")
+    cases = seeded_cases(p, B * num_cases, seed=91)
+    fixed, fn, fv, L = sampling.pack_cases(p.num_nodes, p.max_forces, cases, num_cases)
+    want = gpu_run(p, fixed, fn, fv, L)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    d_in = [t(fixed), t(fn), t(fv), t(L)]
+    nn, n, row0, total = p.num_nodes, p.num_nodes - 1, 3, B + 8
+    spec = (("I", (total, n), torch.float32), ("defl", (total, num_cases, nn), torch.float64),
+            ("rot", (total, num_cases, nn), torch.float64), ("shear", (total, num_cases, n), torch.float32),
+            ("moment", (total, num_cases, n), torch.float32), ("epochs", (total,), torch.int32),
+            ("loss", (total,), torch.float32), ("status", (total,), torch.int32))
+    sets = [{name: torch.full(shape, -7, dtype=dt, device=dev) for name, shape, dt in spec} for _ in range(3)]
+    dests = (_cabi.OpsBeamOptRecordArrays * 3)()
+    for i, st in enumerate(sets):
+        for f, (name, _, _) in zip(("I_values", "deflections", "rotations", "shear", "moment", "epochs", "loss", "status"), spec):
+            setattr(dests[i], f, st[name].data_ptr())
+    ip, fp = ops.pack_params(p)
+    cp = ops._c_params(ip, fp)
+    sched = ops.device_schedule(p, dev)
+    lib = _cabi.lib()
+    assert lib.ops_beamopt_scatter_supported(C.byref(cp)) == 1
+    ws = torch.empty((max(int(lib.ops_beamopt_workspace_bytes(C.byref(cp), B)), 1),), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    rc = lib.ops_beamopt_launch_scatter(C.byref(cp), B, d_in[0].data_ptr(), d_in[1].data_ptr(), d_in[2].data_ptr(),
+                                        d_in[3].data_ptr(), sched.data_ptr(), 3, dests, row0, ws.data_ptr(), ws.numel(),
+                                        stream.cuda_stream)
+    _cabi.check(rc, "ops_beamopt_launch_scatter")
+    torch.cuda.synchronize()
+    for i, st in enumerate(sets):
+        for name, _, _ in spec:
+            got = st[name].cpu().numpy()
+            assert np.array_equal(got[row0:row0 + B], want[name].reshape(got[row0:row0 + B].shape), equal_nan=True), (i, name)
+            assert (got[:row0] == -7).all() and (got[row0 + B:] == -7).all(), (i, name, "rows outside the launch were written")
+
+
 def test_generate_samples_batched_is_a_drop_in():
     """Same entry point, arguments and record schema as the reference's generate_sample."""
     rollers, avail = sampling.fixed_bridge(101)
