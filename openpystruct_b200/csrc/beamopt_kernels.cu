@@ -819,10 +819,21 @@ int ops_beamopt_launch_scatter(const OpsBeamOptParams *p, int64_t B,
                                void *d_workspace, size_t workspace_bytes, void *cuda_stream)
 {
     if (n_dest < 1) return OPS_E_BADARG;
-    // fixed epoch count and more than one peer: chunks of whole rounds + the copy kernel.  With a single peer the copy
-    // inside the kernel is as good as free (2 GPUs: 4.83 ms against 4.81 ms on one), with seven it is 0.85 ms of the step.
+    // Fixed epoch count, more than one peer, a batch of a few rounds: chunks of whole rounds + the copy kernel.  With a
+    // single peer the copy inside the kernel is as good as free (2 GPUs: 4.83 ms against 4.81 ms on one), with seven it
+    // is 0.8 ms of a 1.7-round step.  Over many rounds the in-kernel copies of all rounds but the last hide behind the
+    // following rounds, and the pipeline's chunk granularity costs more than that last burst (1 M beams on 8 GPUs:
+    // 53.0 ms in-kernel, 55.9 ms pipelined), so batches beyond eight rounds keep the in-kernel copy.
     // OPS_SCATTER_IN_KERNEL / OPS_SCATTER_PIPELINED force either form (A/B runs; same results).
-    const bool pipelined = getenv("OPS_SCATTER_PIPELINED") ? true : (getenv("OPS_SCATTER_IN_KERNEL") ? false : n_dest > 2);
+    bool pipelined = n_dest > 2;
+    if (pipelined) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t per_round = (int64_t)sms * 40 / (p && p->num_cases > 0 ? p->num_cases : 1);
+        pipelined = B < 8 * per_round;
+    }
+    if (getenv("OPS_SCATTER_PIPELINED")) pipelined = true;
+    else if (getenv("OPS_SCATTER_IN_KERNEL")) pipelined = false;
     if (n_dest > 1 && n_dest <= lanes::MAX_DEST && dests && B > 0 && p && !p->early_stop && pipelined) {
         BeamConsts k;
         int rc = make_consts(p, &k);
