@@ -77,10 +77,31 @@ struct LaneRegs {
 };
 
 // element index inside its span of slot kk as a double (I2F.F64.U8 with a byte selector: one conversion)
+// Conversions of the pass WITHOUT the XU pipe (I2F / F2F are 8 issue cycles per warp there, the busiest pipe of the
+// kernel; build knob OPS_LANES_XUTRIM, exact either way): a small unsigned integer as 2^52 + k minus 2^52 (one DADD), a
+// positive normal float widened by re-biasing the exponent with integer instructions.
+OPS_HD double small_uint_to_double(unsigned int k)
+{
+#if defined(__CUDA_ARCH__) && defined(OPS_LANES_XUTRIM)
+    return __hiloint2double(0x43300000, (int)k) - 4503599627370496.0;
+#else
+    return (double)k;
+#endif
+}
+OPS_HD double pos_normal_float_to_double(float f)
+{
+#if defined(__CUDA_ARCH__) && defined(OPS_LANES_XUTRIM)
+    const unsigned int b = __float_as_uint(f);
+    return __hiloint2double((int)((b >> 3) + (896u << 20)), (int)(b << 29));
+#else
+    return (double)f;
+#endif
+}
+
 template <int EPL>
 OPS_HD double slot_ke(const LaneRegs<EPL> &rg, int kk)
 {
-    return (double)((rg.ke[kk >> 2] >> (8 * (kk & 3))) & 0xffu);
+    return small_uint_to_double((rg.ke[kk >> 2] >> (8 * (kk & 3))) & 0xffu);
 }
 template <int EPL>
 OPS_HD float &slot_ref(fm::F2 (&a)[LaneRegs<EPL>::NP], int kk) { return (kk & 1) ? a[kk >> 1].y : a[kk >> 1].x; }
@@ -867,7 +888,7 @@ OPS_HD void lane_pass(const BeamConsts &k, int n, LaneRegs<EPL> &rg, const LaneS
             if (NC > 1) {
                 OPS_S { mq[s_] = ls.mq[(long)(2 * p0 + s_) * ls.ls]; ke[s_] = slot_ke<EPL>(rg, 2 * p0 + s_); }
             }
-            OPS_S Id[s_] = (double)((s_ & 1) ? rg.I[p0 + (s_ >> 1)].y : rg.I[p0 + (s_ >> 1)].x);
+            OPS_S Id[s_] = pos_normal_float_to_double((s_ & 1) ? rg.I[p0 + (s_ >> 1)].y : rg.I[p0 + (s_ >> 1)].x);   // (>= clamp_min, finite)
             OPS_S r[s_] = fm::rcp64_a(Id[s_]);
             OPS_S e[s_] = fma(-Id[s_], r[s_], 1.0);           // rcp64_n, stage by stage
             OPS_S e[s_] = fma(e[s_], e[s_], e[s_]);
