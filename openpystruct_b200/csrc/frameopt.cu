@@ -38,6 +38,7 @@ namespace ops {
 namespace frame {
 
 constexpr int THREADS = 128;
+constexpr int WSLOTS = 8;                       // window positions of the trailing update a thread keeps in registers
 constexpr int MAX_DIM = 16;                     // bays, stories <= 16 (the reference draws 1..10)
 
 struct Consts {
@@ -67,7 +68,7 @@ __host__ __device__ inline size_t smem_bytes(int max_bays, int max_stories)
     const size_t n = (size_t)num_dofs(max_bays, max_stories), hb = (size_t)half_bw(max_bays), ne = (size_t)num_elems(max_bays, max_stories);
     size_t doubles = (hb + 1) * n      // lower band of K, then of its Cholesky factor
                      + 3 * n           // load vector, right-hand side / solution, reciprocal pivots
-                     + (hb + 1)        // scaled column of the current elimination step
+                     + 2 * (hb + 1)    // scaled column of the current elimination step (double-buffered)
                      + 2 * ne;         // M, V
     size_t floats = 7 * ne;            // I, m, v, d, q, g, (spare)
     size_t bytes = doubles * 8 + floats * 4 + (hb + 1) * (hb + 2);   // + (r, c) pair table of the trailing update
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(THREADS) frameopt_kernel(const Consts k, const
         double *u = f0 + n;
         double *rinv = u + n;
         double *lcol = rinv + n;
-        double *Mv = lcol + (hb + 1);
+        double *lcol2 = lcol + (hb + 1);
+        double *Mv = lcol2 + (hb + 1);
         double *Vv = Mv + ne;
         float *If = reinterpret_cast<float *>(Vv + ne);
         float *mf = If + ne, *vf = mf + ne, *df = vf + ne, *qf = df + ne, *gf = qf + ne;
@@ -123,6 +125,22 @@ __global__ void __launch_bounds__(THREADS) frameopt_kernel(const Consts k, const
         }
         if (tid == 0) { s_flag[0] = valid ? 0 : 1; s_flag[1] = 0; s_flag[2] = 0; s_flag[3] = 0; s_best = INFINITY; }
         __syncthreads();
+        // the trailing update's fixed window positions of this thread (warps 1..3): slot s_ = entry s_ * 96 + (tid - 32) of
+        // the pair table shifted by one, i.e. (r, c) with 2 <= c <= r; r = 0 marks an unused slot
+        const int warp = tid >> 5, lane = tid & 31;
+        unsigned int wr[WSLOTS / 4], wc[WSLOTS / 4];
+        int woff[WSLOTS];
+#pragma unroll
+        for (int w_ = 0; w_ < WSLOTS / 4; ++w_) { wr[w_] = 0u; wc[w_] = 0u; }
+#pragma unroll
+        for (int s_ = 0; s_ < WSLOTS; ++s_) {
+            const int i = s_ * (THREADS - 32) + (tid - 32);
+            int r = 0, c = 0;
+            if (warp > 0 && i < (hb - 1) * hb / 2) { r = pairs[2 * i] + 1; c = pairs[2 * i + 1] + 1; }
+            wr[s_ >> 2] |= (unsigned int)r << (8 * (s_ & 3));
+            wc[s_ >> 2] |= (unsigned int)c << (8 * (s_ & 3));
+            woff[s_] = (r - c) * n + c;
+        }
         {
             const double w = k.vertical, L = k.bay_width;
             for (int nd = tid; nd < nnodes; nd += THREADS) {      // elevated node (s, b), s = 1 .. stories
@@ -176,40 +194,85 @@ __global__ void __launch_bounds__(THREADS) frameopt_kernel(const Consts k, const
                 ab[(size_t)1 * n + j0 + 1] = d21;                                            // A[j0+2][j0+1]
             }
             __syncthreads();
-            // ---- band Cholesky + forward substitution, column by column
-            for (int j = 0; j < n; ++j) {
-                const int lim = (n - 1 - j < hb) ? n - 1 - j : hb;
-                const double piv = ab[j];
-                const double ri = rsqrt(piv);
-                if (tid == 0) {
-                    if (!(piv > 0.0)) s_flag[0] = 1;
-                    rinv[j] = ri;
-                    u[j] = u[j] * ri;                                    // y_j
+            // ---- band Cholesky + forward substitution, column by column, ONE CTA barrier per column.
+            // Warp 0 owns the critical path: it scales column j (pivot, reciprocal square root, y_j), and in the trailing
+            // update it takes exactly the entries it needs next -- column j + 1 and the right-hand side -- so that it can
+            // scale column j + 1 without waiting for anybody; warps 1..3 apply column j to the rest of the window
+            // (columns j + 2 ...) meanwhile, each thread on a FIXED set of window positions (r, c) it worked out once per
+            // frame (registers; eight per thread cover half bandwidths up to 38, the pair table serves the rest), so
+            // that its loads are issued back to back instead of one dependent chain per entry.  The scaled column
+            // travels through a double-buffered `lcol`; the barrier of step j + 1 is what orders the other warps'
+            // updates of step j before anything of step j + 1 touches them.  Every entry receives the same rank-1
+            // updates in the same (column) order as a plain right-looking sweep: same bits.
+            {
+                for (int j = 0; j < n; ++j) {
+                    const int lim = (n - 1 - j < hb) ? n - 1 - j : hb;
+                    double *lc = (j & 1) ? lcol2 : lcol;
+                    double yj = 0.0;
+                    if (warp == 0) {
+                        const double piv = ab[j];
+                        const double ri = rsqrt(piv);
+                        yj = u[j] * ri;
+                        __syncwarp();                                    // (every lane has read u[j])
+                        if (lane == 0) {
+                            if (!(piv > 0.0)) s_flag[0] = 1;
+                            rinv[j] = ri;
+                            u[j] = yj;
+                        }
+                        for (int t = lane + 1; t <= lim; t += 32) {
+                            const double l = ab[(size_t)t * n + j] * ri;
+                            ab[(size_t)t * n + j] = l;
+                            lc[t] = l;
+                        }
+                    }
+                    __syncthreads();
+                    if (warp == 0) {
+                        // column j + 1 of the window: A[j + r][j + 1] -= l_r l_1 ; right-hand side: u[j + t] -= l_t y_j
+                        if (lim >= 1) {
+                            const double l1 = lc[1];
+                            for (int r = lane + 1; r <= lim; r += 32) {
+                                const double lr = lc[r];
+                                ab[(size_t)(r - 1) * n + j + 1] = fma(-lr, l1, ab[(size_t)(r - 1) * n + j + 1]);
+                                u[j + r] = fma(-lr, yj, u[j + r]);
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        // window positions (r, c), 2 <= c <= r <= lim: this thread's fixed slots first
+                        double a_[WSLOTS], lr_[WSLOTS], lc_[WSLOTS];
+#pragma unroll
+                        for (int s_ = 0; s_ < WSLOTS; ++s_) {
+                            const int r = (int)((wr[s_ >> 2] >> (8 * (s_ & 3))) & 0xffu);
+                            const bool on = r >= 2 && r <= lim;
+                            const int c = (int)((wc[s_ >> 2] >> (8 * (s_ & 3))) & 0xffu);
+                            lr_[s_] = on ? lc[r] : 0.0;
+                            lc_[s_] = on ? lc[c] : 0.0;
+                            a_[s_] = on ? ab[(size_t)woff[s_] + j] : 0.0;
+                        }
+#pragma unroll
+                        for (int s_ = 0; s_ < WSLOTS; ++s_) {
+                            const int r = (int)((wr[s_ >> 2] >> (8 * (s_ & 3))) & 0xffu);
+                            if (r >= 2 && r <= lim) ab[(size_t)woff[s_] + j] = fma(-lr_[s_], lc_[s_], a_[s_]);
+                        }
+                        const int np = (lim - 1) * lim / 2;
+                        for (int i = tid - 32 + WSLOTS * (THREADS - 32); i < np; i += THREADS - 32) {
+                            const int r = pairs[2 * i] + 1, c = pairs[2 * i + 1] + 1;
+                            ab[(size_t)(r - c) * n + j + c] = fma(-lc[r], lc[c], ab[(size_t)(r - c) * n + j + c]);
+                        }
+                    }
                 }
-                if (tid >= 1 && tid <= lim) {
-                    const double l = ab[(size_t)tid * n + j] * ri;
-                    ab[(size_t)tid * n + j] = l;
-                    lcol[tid] = l;
-                }
-                __syncthreads();
-                const double yj = u[j];
-                const int np = lim * (lim + 1) / 2;
-                for (int i = tid; i < np; i += THREADS) {
-                    const int r = pairs[2 * i], c = pairs[2 * i + 1];
-                    ab[(size_t)(r - c) * n + j + c] = fma(-lcol[r], lcol[c], ab[(size_t)(r - c) * n + j + c]);
-                }
-                if (tid >= 1 && tid <= lim) u[j + tid] = fma(-lcol[tid], yj, u[j + tid]);
                 __syncthreads();
             }
-            // ---- back substitution: one warp, fixed-order shuffle reduction
-            if (tid < 32) {
+            // ---- back substitution L^T x = y by columns (the order of LAPACK's dtbsv): x_j = y_j / l_jj, then
+            // y_{j-d} -= l_{j, j-d} x_j for the <= hb entries of row j of the factor -- one warp, no reduction
+            if (warp == 0) {
                 for (int j = n - 1; j >= 0; --j) {
-                    const int lim = (n - 1 - j < hb) ? n - 1 - j : hb;
-                    double acc = 0.0;
-                    for (int d = 1 + tid; d <= lim; d += 32) acc = fma(ab[(size_t)d * n + j], u[j + d], acc);
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (tid == 0) u[j] = (u[j] - acc) * rinv[j];
+                    const double xj = u[j] * rinv[j];
+                    const int lim = j < hb ? j : hb;
+                    __syncwarp();                                        // (every lane has read u[j])
+                    if (lane == 0) u[j] = xj;
+                    for (int d = lane + 1; d <= lim; d += 32)
+                        u[j - d] = fma(-ab[(size_t)d * n + (j - d)], xj, u[j - d]);
                     __syncwarp();
                 }
             }
