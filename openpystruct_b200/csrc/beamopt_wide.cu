@@ -180,6 +180,7 @@ beamopt_wide_kernel(const BeamConsts k, const long long B, const OptPtrs p, cons
     SweepConsts sc;
     sc.G2 = 0.0; sc.H2 = 0.0; sc.neg_step = 0.0f; sc.bc2_sqrt = 1.0f; sc.rbc = 1.0f;
     LaneCtx<LPB> cx;
+    SegStatics st = {{0.0, 0.0, 0.0}};
     long long b = -1;
     int state = ST_NEED, t = 0, counter = 0, bad = 0;
     double best = INFINITY;
@@ -202,6 +203,7 @@ beamopt_wide_kernel(const BeamConsts k, const long long B, const OptPtrs p, cons
             }
             __syncwarp(gmask);
             bad = wide_fetch(k, p.L[b], ws, fb);
+            wide_fetch_statics<LPB>(ws, l, st);
             sc.G2 = 6.0 * fb.wl2h; sc.H2 = 3.0 * fb.wl2h;
             t = 0; counter = 0; best = INFINITY; lossf = NAN;
             if (bad != 0 || k.max_epochs <= 0) {
@@ -221,7 +223,7 @@ beamopt_wide_kernel(const BeamConsts k, const long long B, const OptPtrs p, cons
             sc.neg_step = __ldg(p.sched + 2 * t);
             sc.bc2_sqrt = __ldg(p.sched + 2 * t + 1);
             sc.rbc = fm::rcp_r(sc.bc2_sqrt);
-            rc = wide_solve<LPB>(fb, ws, l);
+            rc = wide_solve<LPB>(fb, ws, l, st);
         }
         __syncwarp();
         const int cur = run ? (t & 1) : 0;

@@ -52,13 +52,17 @@ constexpr int NSPAN = FLEX_MAXS - 1;
 constexpr int DUMMY = NSPAN;                    // span id of overhang elements and padding
 constexpr int NSUM = 5;                         // R0, R1, R2, G, Q of beamopt_lanes.cuh
 constexpr int MAXSEG = 16;                      // spans + loads + overhang + padding <= 5 + 8 + 1 + 1
-constexpr int ROW = 12;                         // doubles per segment row
-// row = six 16-byte pairs, fetched with 128-bit shared loads in the order the sweep needs them
+// row = 16-byte pairs, fetched with 128-bit shared loads in the order the sweep needs them.  The statics
+// {c0, c1, q0} a row is rewritten FROM every epoch: LPB = 8 keeps them behind the row (12 doubles); LPB = 32 --
+// segment s is rewritten by lane s (wide_solve) -- keeps them in that lane's registers (SegStatics, rows of 8
+// doubles): 512 B per beam less, which is the twelfth 1000-element beam of an SM.
+template <int LPB>
+OPS_HD constexpr int row_doubles() { return LPB == 32 ? 8 : 12; }
 enum { R_NA = 0, R_C0 = 1,                      // first node of the span; this epoch's C0
        R_C1 = 2, R_QC = 3,                      // this epoch's C1, Qc
        R_G1 = 4, R_H1 = 5,                      // PASS 1 weights G = (G2 ke + G1) ke + G0, g2 = (H2 ke + H1) ke + H0
        R_G0 = 6, R_H0 = 7,
-       R_B0 = 8, R_B1 = 9, R_BQ = 10 };         // statics {c0, c1, q0}
+       R_B0 = 8, R_B1 = 9, R_BQ = 10 };         // LPB = 8: statics {c0, c1, q0}
 struct alignas(16) Pair {                       // two doubles moved with one 128-bit shared access
     double x, y;
 };
@@ -70,7 +74,7 @@ struct WideStore {
     float *I0, *m, *v;                          // [K * LPB], element order; I is double-buffered: I0 + (epoch & 1) * el
     int el;                                     // K * LPB
     unsigned char *seg;                         // [K * LPB]: segment id | span id << 4 | (a span closes in this slot) << 7
-    double *rows;                               // [MAXSEG * ROW]
+    double *rows;                               // [MAXSEG * row_doubles<LPB>()]
     double *tot;                                // [NSPAN * NSUM] span sums of the inertias about to be analysed
     double *gd;                                 // Moh, Qoh
     int *gi;                                    // [GI_INTS]
@@ -118,7 +122,7 @@ template <int LPB>
 OPS_HD size_t wide_beam_bytes(int n)
 {
     const size_t el = (size_t)wide_slots<LPB>(n) * LPB;
-    size_t b = (size_t)(MAXSEG * ROW + NSPAN * NSUM + 2 + FlexStore::NUM_DOUBLES) * 8;   // doubles first
+    size_t b = (size_t)(MAXSEG * row_doubles<LPB>() + NSPAN * NSUM + 2 + FlexStore::NUM_DOUBLES) * 8;   // doubles first
     b += 4 * el * 4;
     b += (size_t)(GI_INTS + FlexStore::NUM_INTS) * 4;
     b += el;
@@ -129,7 +133,7 @@ OPS_HD void wide_carve(unsigned char *base, int n, WideStore &ws)
 {
     const size_t el = (size_t)wide_slots<LPB>(n) * LPB;
     double *d = reinterpret_cast<double *>(base);
-    ws.rows = d; d += MAXSEG * ROW;
+    ws.rows = d; d += MAXSEG * row_doubles<LPB>();
     ws.tot = d; d += NSPAN * NSUM;
     ws.gd = d; d += 2;
     ws.fs.sd = d; d += FlexStore::NUM_DOUBLES;
@@ -166,15 +170,16 @@ OPS_HD int wide_setup(const BeamConsts &k, double L, FixedFn fixed, const int *f
         const double cG = fma(3.0, fb.wl2h, -2.0 * fb.corr), cH = fma(2.0, fb.wl2h, -fb.corr);
         const double k3Le = 3.0 * Le, k2Le = 2.0 * Le;
         auto emit = [&](int ea, int span, int na, double c0, double c1, double q0) {
+            constexpr int ROW = row_doubles<LPB>();
             double *r = ws.rows + ns * ROW;
             const bool live = span != DUMMY;
-            r[R_B0] = c0; r[R_B1] = c1; r[R_BQ] = q0; r[R_NA] = (double)na;
-            r[R_C0] = c0; r[R_C1] = c1; r[R_QC] = q0;
+            r[R_NA] = (double)na;
+            r[R_C0] = c0; r[R_C1] = c1; r[R_QC] = q0;            // (LPB = 32: the statics, until wide_fetch_statics has taken them)
+            if (ROW > 8) { r[R_B0] = c0; r[R_B1] = c1; r[R_BQ] = q0; r[11] = 0.0; }
             r[R_G1] = live ? fma(6.0, c1, k3Le * fb.wl) : 0.0;
             r[R_G0] = live ? fma(6.0, c0, fma(k3Le, q0, cG)) : 0.0;
             r[R_H1] = live ? fma(3.0, c1, k2Le * fb.wl) : 0.0;
             r[R_H0] = live ? fma(3.0, c0, fma(k2Le, q0, cH)) : 0.0;
-            r[11] = 0.0;
             ws.gi[GI_SEGSTART + ns] = ea;
             ws.gi[GI_SEGSPAN + ns] = span;
             ++ns;
@@ -228,6 +233,22 @@ OPS_HD int wide_fetch(const BeamConsts &k, double L, const WideStore &ws, FlexBe
     fb.m = ws.gi[GI_M]; fb.last = ws.gi[GI_LAST]; fb.nloads = ws.gi[GI_NLOADS];
     fb.Moh = ws.gd[0]; fb.Qoh = ws.gd[1];
     return ws.gi[GI_RC];
+}
+
+// LPB = 32: statics {c0, c1, q0} of segment l, the one lane l rewrites -- registers on the device
+struct SegStatics {
+    double b[3];
+};
+// every lane, after wide_setup is visible and before the first wide_solve (the rows still hold the statics)
+template <int LPB>
+OPS_HD void wide_fetch_statics(const WideStore &ws, int l, SegStatics &st)
+{
+    static_assert(MAXSEG <= 32, "one segment per lane");
+    st.b[0] = st.b[1] = st.b[2] = 0.0;
+    if (LPB == 32 && l < ws.gi[GI_NSEG]) {
+        const double *r = ws.rows + l * row_doubles<LPB>();
+        st.b[0] = r[R_C0]; st.b[1] = r[R_C1]; st.b[2] = r[R_QC];
+    }
 }
 
 template <int LPB>
@@ -434,7 +455,7 @@ OPS_HD void sweep_batch(const BeamConsts &k, const FlexBeam &fb, const WideShape
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        row[i] = reinterpret_cast<const Pair *>(ws.rows + (sb[i] & 0x0fu) * ROW);
+        row[i] = reinterpret_cast<const Pair *>(ws.rows + (sb[i] & 0x0fu) * row_doubles<LPB>());
         nc[i] = row[i][0];
     }
 #pragma unroll
@@ -632,7 +653,7 @@ OPS_HD float wide_loss_arrays(const BeamConsts &k, const WideShape &sh, const fl
 // rows and lane 0 keeps a, b, p and the support moments for the displacement record.  Returns 1 on a
 // bad pivot.
 template <int LPB>
-OPS_HD int wide_solve(const FlexBeam &fb, const WideStore &ws, int l)
+OPS_HD int wide_solve(const FlexBeam &fb, const WideStore &ws, int l, const SegStatics &st)
 {
     const int m = fb.m;
     double a[NSPAN], b[NSPAN], c[NSPAN], p[NSPAN], q[NSPAN], dx[NSPAN];
@@ -689,10 +710,11 @@ OPS_HD int wide_solve(const FlexBeam &fb, const WideStore &ws, int l)
             ml = hit ? MS[j] : ml;
             t1 = hit ? (MS[j + 1] - MS[j]) * dx[j] : t1;
         }
-        double *r = ws.rows + s * ROW;
-        r[R_C0] = r[R_B0] + ml;
-        r[R_C1] = r[R_B1] + t1;
-        r[R_QC] = r[R_BQ] + t1 * fb.invLe;
+        double *r = ws.rows + s * row_doubles<LPB>();
+        const bool in_regs = LPB == 32;                          // (then s = l: one trip)
+        r[R_C0] = (in_regs ? st.b[0] : r[R_B0]) + ml;
+        r[R_C1] = (in_regs ? st.b[1] : r[R_B1]) + t1;
+        r[R_QC] = (in_regs ? st.b[2] : r[R_BQ]) + t1 * fb.invLe;
     }
     if (l == 0) {
 #pragma unroll
@@ -720,7 +742,7 @@ OPS_HD void wide_emit_lane(const FlexBeam &fb, const WideShape &sh, const WideSt
         if (e < sh.n) {
             float V = 0.0f, M = 0.0f;
             if (fields) {
-                const double *r = ws.rows + (ws.seg[e] & 0x0fu) * ROW;
+                const double *r = ws.rows + (ws.seg[e] & 0x0fu) * row_doubles<LPB>();
                 const double ke = (double)e - r[R_NA];
                 const double Mc = fma(fma(fb.wl2h, ke, r[R_C1]), ke, r[R_C0]);
                 const double Qv = fma(fb.wl, ke, r[R_QC]);

@@ -604,6 +604,7 @@ static int wide_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, con
     WideStore ws;
     wide_carve<LPB>(reinterpret_cast<unsigned char *>(raw.data()), n, ws);
     static LaneCtx<LPB> cx[LPB];
+    static SegStatics st[LPB];
     for (int64_t b = 0; b < B; ++b) {
         int fnode[FLEX_MAXF];
         double fval[FLEX_MAXF];
@@ -615,6 +616,7 @@ static int wide_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, con
         wide_setup<LPB>(k, L[b], [&](int i) { return fx[i] != 0; }, fnode, fval, ws);
         FlexBeam fb;
         int bad = wide_fetch(k, L[b], ws, fb);
+        for (int l = 0; l < LPB; ++l) wide_fetch_statics<LPB>(ws, l, st[l]);
         const bool setup_bad = bad != 0;
         SweepConsts sc;
         sc.G2 = 6.0 * fb.wl2h; sc.H2 = 3.0 * fb.wl2h; sc.neg_step = 0.0f; sc.bc2_sqrt = 1.0f; sc.rbc = 1.0f;
@@ -629,7 +631,7 @@ static int wide_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, con
         while (!done) {
             sc.neg_step = sched[2 * t]; sc.bc2_sqrt = sched[2 * t + 1]; sc.rbc = 1.0f / sc.bc2_sqrt;
             int rc = 0;
-            for (int l = LPB - 1; l >= 0; --l) rc |= wide_solve<LPB>(fb, ws, l);
+            for (int l = LPB - 1; l >= 0; --l) rc |= wide_solve<LPB>(fb, ws, l, st[l]);
             wide_host_sweep<LPB>(k, fb, sh, ws, true, ws.I0 + (t & 1) * ws.el, ws.I0 + ((t + 1) & 1) * ws.el, sc, cx);
             float acc[3][LPB], left[3][LPB];
             for (int w = 0; w < 3; ++w)
