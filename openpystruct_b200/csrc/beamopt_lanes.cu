@@ -106,7 +106,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
 
     double *lane_d = reinterpret_cast<double *>(smem_raw);
     double *tab_d = lane_d + (size_t)lane_doubles(EPL, NC) * T;
-    const int GS = G;
+    const int GS = group_stride(G);
     double *grp_d = tab_d + (size_t)TAB_SLOTS * G;
     int *grp_i = reinterpret_cast<int *>(grp_d + (size_t)GROUP_DOUBLES * GS);
     LaneStore ls;
@@ -227,8 +227,9 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             neg_step = __ldg(p.sched + 2 * t);
             bc2_sqrt = __ldg(p.sched + 2 * t + 1);
         }
+        Pair mqk[NC > 1 ? EPL : 1];                                 // teams: {M0, Q0} from the sums to the forces, in registers
         if constexpr (NC > 1) {
-            if (run) team_pass1<EPL, NC>(rg, ls, pc, case_id);      // P1: this case's sums from the team's inertias
+            if (run) team_pass1<EPL, NC>(rg, ls, pc, case_id, mqk); // P1: this case's sums from the team's inertias
         }
         __syncwarp();
         if (run) lane_reduce(l, fb.m, ls, gs);
@@ -241,7 +242,7 @@ beamopt_lanes_kernel(const BeamConsts k, const long long B, const OptPtrs p)
             if (run) lane_pass<EPL, NC, NBK>(k, n, rg, ls, gs, pc, fb.invLe, l, case_id, neg_step, bc2_sqrt, stage_I);
             __syncwarp();
         } else {
-            if (run) lane_case_squares<EPL>(rg, ls, gs, fb.invLe);
+            if (run) lane_case_squares<EPL>(rg, ls, gs, fb.invLe, mqk);
             if (NC * LPB <= 32) __syncwarp();
             else if (run) team_sync<NC>(team_mask, barrier_id);     // whole warps belong to one team: uniform
             if (run) team_owner_update<EPL, NC>(k, rg, ls, case_id, neg_step, bc2_sqrt);     // P2
@@ -314,9 +315,10 @@ int lanes_plan(const BeamConsts &k, int num_cases, int64_t B, int sms, int smem_
     const int team_threads = num_cases * LPB;                     // whole teams per CTA (and whole warps per team)
     const int quantum = team_threads > 32 ? team_threads : 32;
     T = T / quantum * quantum;
+    while (T >= quantum && cta_smem_bytes(T / LPB, pl->epl, num_cases) > (size_t)smem_optin) T -= quantum;   // (the padded stride)
     if (T < quantum) return -2;
     pl->threads = T;
-    pl->smem_bytes = per_group * (T / LPB);
+    pl->smem_bytes = cta_smem_bytes(T / LPB, pl->epl, num_cases);
     const long per_cta = T / team_threads;
     long want = (long)((B + per_cta - 1) / per_cta);
     pl->blocks = (int)(want < sms ? want : sms);

@@ -58,6 +58,19 @@ constexpr int GX_DOUBLES = 2;                   // Moh, Qoh
 constexpr int GX_INTS = 6;                      // m, last, nloads, setup status, beam index of the team (lo, hi)
 constexpr int GROUP_DOUBLES = FlexStore::NUM_DOUBLES + GX_DOUBLES;   // strided [slot][group] columns (+ TAB_SLOTS contiguous)
 constexpr int GROUP_INTS = FlexStore::NUM_INTS + GX_INTS;
+// Stride of the [slot][group] columns (register / shared-memory instances).  The five lanes that publish a, b, c, p, q of
+// their span (lane_reduce) write the slots 7 j + X: with a stride of G = 40 or 48 groups they fall on two banks (6
+// wavefronts per store instead of 2; ncu, profiles/r02_ncu_summary.md); a stride = 12 (mod 16) puts consecutive spans
+// 8 banks apart (measured: +1.1 % on many-round batches and on the 8-case teams, profiles/r02_group_stride_ab.txt).
+// Build knob OPS_LANES_NO_GSPAD (A/B).
+OPS_HD constexpr int group_stride(int G)
+{
+#ifdef OPS_LANES_NO_GSPAD
+    return G;
+#else
+    return G + (((12 - G) % 16) + 16) % 16;
+#endif
+}
 
 // multi-case teams: pair j of the lane's slots is OWNED by group j % NC (its fp32 chain, Adam state and exchange rows)
 OPS_HD constexpr int team_owned_pairs(int epl, int nc) { return ((epl + 1) / 2 + nc - 1) / nc; }
@@ -65,6 +78,12 @@ constexpr int XB_ROWS = 4;                      // exchange rows of an owned pai
 OPS_HD constexpr int lane_doubles(int epl, int nc)
 {
     return 2 * epl + SCR_SLOTS + (nc > 1 ? epl + XB_ROWS * team_owned_pairs(epl, nc) : 0);
+}
+// shared memory of a CTA of G groups (lanes_plan and the kernel's carve-up agree on this)
+OPS_HD constexpr size_t cta_smem_bytes(int G, int epl, int num_cases)
+{
+    return (size_t)G * ((size_t)LPB * 8 * lane_doubles(epl, num_cases) + (size_t)TAB_SLOTS * 8) +
+           (size_t)group_stride(G) * ((size_t)GROUP_DOUBLES * 8 + (size_t)GROUP_INTS * 4);
 }
 
 template <int EPL>
@@ -687,14 +706,24 @@ OPS_HD void element_forces(const LaneRegs<EPL> &rg, const LaneStore &ls, const G
 #endif
 constexpr int NBP = OPS_LANES_NBP;
 
-// multi-case kernels, before the pass: M^2, V^2 of this group's load case into the exchange column
+// multi-case kernels, before the pass: M^2, V^2 of this group's load case into the exchange column.  mqk: {M0, Q0} of
+// the lane's first TEAM_KEEP slots, kept in registers since team_pass1 of the same epoch fetched them (a team member
+// carries one or two pairs of optimiser state, not seven; the team kernel issues 581 shared-memory wavefronts per
+// warp-epoch against ~400 of the single-case kernel, profiles/r02_ncu_summary.md)
+#ifndef OPS_TEAM_KEEP
+#define OPS_TEAM_KEEP 8
+#endif
+// slots whose {M0, Q0} stay in registers, the rest is fetched again: all 13 spill; measured 0 / 8 / 13 kept:
+// 343 k / 350 k / 345 k beams/s with 8 load cases (profiles/r02_team_keep_ab.txt)
+constexpr int TEAM_KEEP = OPS_TEAM_KEEP;
 template <int EPL>
-OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe)
+OPS_HD void lane_case_squares(const LaneRegs<EPL> &rg, const LaneStore &ls, const GroupStore &gs, double invLe,
+                              const Pair (&mqk)[EPL])
 {
 #pragma unroll
     for (int kk = 0; kk < EPL; ++kk) {
         double Mc, Qv;
-        element_forces<EPL>(rg, ls, gs, invLe, kk, Mc, Qv);
+        element_forces_mq<EPL>(rg, gs, invLe, kk, kk < TEAM_KEEP ? mqk[kk] : ls.mq[(long)kk * ls.ls], Mc, Qv);
         const float Mf = (float)Mc, Vf = (float)Qv;
         PairF x;
         x.c = Mf * Mf; x.h = Vf * Vf;
@@ -946,9 +975,10 @@ OPS_HD void team_init(const BeamConsts &k, int n, const LaneStore &ls, int l, in
     }
 }
 
-// P1: the five sums of this group's case from the team's current inertias (stage-major batches of six slots)
+// P1: the five sums of this group's case from the team's current inertias (stage-major batches of six slots);
+// the {M0, Q0} it fetches stay in mqk for lane_case_squares
 template <int EPL, int NC>
-OPS_HD void team_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, int case_id)
+OPS_HD void team_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1Consts &pc, int case_id, Pair (&mqk)[EPL])
 {
     constexpr int SB = 6;
     SpanSums acc = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -962,6 +992,7 @@ OPS_HD void team_pass1(const LaneRegs<EPL> &rg, const LaneStore &ls, const Pass1
             const fm::F2 In = *team_row<NC>(ls, case_id, kk >> 1, 3);
             Id[s_] = (double)((kk & 1) ? In.y : In.x);
             mq[s_] = ls.mq[(long)kk * ls.ls];
+            if (kk < TEAM_KEEP) mqk[kk] = mq[s_];
             ke[s_] = slot_ke<EPL>(rg, kk);
         }
         OPS_T r[s_] = fm::rcp64_a(Id[s_]);

@@ -282,14 +282,15 @@ static int lanes_run(const BeamConsts &k, int64_t B, const uint8_t *fixed_uy, co
         while (!done) {
             neg_step = sched[2 * t]; bc2_sqrt = sched[2 * t + 1];
             int rc = 0;
+            static Pair mqk[NC][LPB][EPL];                         // (registers of the lane on the device)
             if constexpr (NC > 1) {
                 for (int c = 0; c < NC; ++c)
-                    for (int l = 0; l < LPB; ++l) team_pass1<EPL, NC>(rg[c][l], ls[c][l], pass1_consts(fb[c]), c);
+                    for (int l = 0; l < LPB; ++l) team_pass1<EPL, NC>(rg[c][l], ls[c][l], pass1_consts(fb[c]), c, mqk[c][l]);
             }
             for (int c = 0; c < NC; ++c) {
                 for (int l = 0; l < LPB; ++l) lane_reduce(l, fb[c].m, ls[c][l], gs[c]);
                 for (int l = LPB - 1; l >= 0; --l) rc |= group_solve(fb[c], gs[c], l);
-                if (NC > 1) for (int l = 0; l < LPB; ++l) lane_case_squares<EPL>(rg[c][l], ls[c][l], gs[c], fb[c].invLe);
+                if (NC > 1) for (int l = 0; l < LPB; ++l) lane_case_squares<EPL>(rg[c][l], ls[c][l], gs[c], fb[c].invLe, mqk[c][l]);
             }
             float lv[NC][LPB];
             const bool stage_I = (t + 1 >= k.max_epochs) || (k.early_stop && counter + 1 >= k.patience);
