@@ -28,11 +28,69 @@ _DENSE = ("I_values", "shear_forces", "bending_moments", "node_positions", "rota
 _SCALAR = ("num_nodes", "L")
 
 
-def columnar_from_run(params: BeamOptParams, cases, out: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+def _ragged_packed(tags, values, dtype, pad):
+    """tags: i32 [records, width0] 1-based, 0 = unused (used slots first); values: same shape or None."""
+    lens = np.count_nonzero(tags, axis=1).astype(np.int32)
+    width = int(lens.max()) if len(lens) else 0
+    src = tags if values is None else values
+    vals = np.where(np.arange(width)[None, :] < lens[:, None], src[:, :width], pad).astype(dtype)
+    return vals, lens
+
+
+def _x_locations(col, node_positions, nn):
+    """roller / force x positions = node_positions[node - 1] (SingleCore:234-235), NaN-padded like the node lists."""
+    n_rec = len(col["roller_nodes"])
+
+    def locate(nodes):
+        if not n_rec:
+            return np.zeros((0, 0))
+        return np.where(nodes >= 0, np.take_along_axis(node_positions, np.clip(nodes - 1, 0, nn - 1), axis=1), np.nan)
+    col["roller_x_locations"], col["roller_x_locations_len"] = locate(col["roller_nodes"]), col["roller_nodes_len"]
+    col["force_x_locations"], col["force_x_locations_len"] = locate(col["force_nodes"]), col["force_nodes_len"]
+
+
+def case_columns(params: BeamOptParams, cases, keep_b=None) -> Dict[str, np.ndarray]:
+    """The record keys that depend on the SAMPLED CASES alone (geometry, supports, loads) of a
+    ``sampling.PackedCases``: everything of ``columnar_from_run`` but the kernel outputs.  ``keep_b``: the beams to
+    keep (None = all).  ``stream_columnar`` computes this on the sampler's thread while the GPU runs the previous
+    batch, so that nothing but views of the kernel outputs is left for the critical path."""
+    C = params.num_cases
+    nn = params.num_nodes
+    B = len(cases) // C
+    all_ok = keep_b is None
+    if all_ok:
+        keep_b = np.arange(B)
+    rec = (keep_b[:, None] * C + np.arange(C)[None, :]).reshape(-1)          # record index = beam * C + case
+    pick_b = (lambda a: np.asarray(a)[:B]) if all_ok else (lambda a: np.asarray(a)[keep_b])
+    pick_r = (lambda a: a) if all_ok else (lambda a: a[rec])
+    rep = (lambda a: a) if C == 1 else (lambda a: np.repeat(a, C, axis=0))
+    L = pick_b(np.asarray(cases.L, np.float64))
+    node_positions = np.zeros((0, nn))
+    if len(L) and np.all(L == L[0]):                                         # fixed bridge: one row, broadcast (read-only view)
+        node_positions = np.broadcast_to(np.linspace(0, L[0], nn), (len(L), nn))
+    elif len(L):                                                             # np.linspace(0, L, nn) bit for bit
+        step = L / (nn - 1)
+        node_positions = np.arange(nn)[None, :] * step[:, None]
+        node_positions[:, -1] = L
+    col = {"node_positions": rep(node_positions), "num_nodes": np.full(len(rec), nn, np.int32), "L": rep(L)}
+    first = (rec // C) * C                                                   # supports shared by the cases of a beam
+    col["roller_nodes"], col["roller_nodes_len"] = _ragged_packed(
+        cases.roller_tags if (all_ok and C == 1) else cases.roller_tags[first], None, np.int32, -1)
+    ft = pick_r(cases.force_tags)
+    col["force_nodes"], col["force_nodes_len"] = _ragged_packed(ft, None, np.int32, -1)
+    fv = pick_r(cases.force_vals.reshape(len(cases), -1))
+    col["force_values"], col["force_values_len"] = _ragged_packed(ft, fv, np.float64, np.nan)
+    _x_locations(col, col["node_positions"], nn)
+    return col
+
+
+def columnar_from_run(params: BeamOptParams, cases, out: Dict[str, np.ndarray],
+                      case_cols: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
     """Kernel outputs + the sampled cases -> one array per key of the reference record (failed beams
     dropped, MultiCore:265).  Ragged keys are (values, lengths) pairs padded with NaN / -1.
     ``cases``: the list of ``sampling.sample_case`` tuples, or a ``sampling.PackedCases`` (native sampler), which is
-    consumed as arrays -- no per-record Python objects."""
+    consumed as arrays -- no per-record Python objects.  ``case_cols``: ``case_columns(params, cases)`` computed ahead
+    (used when no beam has to be dropped)."""
     from .sampling import PackedCases
     C = params.num_cases
     packed = isinstance(cases, PackedCases)
@@ -41,21 +99,21 @@ def columnar_from_run(params: BeamOptParams, cases, out: Dict[str, np.ndarray]) 
     all_ok = keep_b.size == B                                                # the common case: nothing to drop, no gather copies
     rec = (keep_b[:, None] * C + np.arange(C)[None, :]).reshape(-1)          # record index = beam * C + case
     pick_b = (lambda a: np.asarray(a)[:B]) if all_ok else (lambda a: np.asarray(a)[keep_b])
-    pick_r = (lambda a: a) if all_ok else (lambda a: a[rec])
     rep = (lambda a: a) if C == 1 else (lambda a: np.repeat(a, C, axis=0))
     nn = params.num_nodes
+    col = {
+        "I_values": rep(pick_b(out["I"])),
+        "shear_forces": pick_b(out["shear"]).reshape(len(rec), -1),
+        "bending_moments": pick_b(out["moment"]).reshape(len(rec), -1),
+        "rotations": pick_b(out["rot"]).reshape(len(rec), -1),
+        "deflections": pick_b(out["defl"]).reshape(len(rec), -1),
+    }
     if packed:
-        L = pick_b(np.asarray(cases.L, np.float64))
-        node_positions = np.zeros((0, nn))
-        if len(L) and np.all(L == L[0]):                                     # fixed bridge: one row, broadcast (read-only view)
-            node_positions = np.broadcast_to(np.linspace(0, L[0], nn), (len(L), nn))
-        elif len(L):                                                         # np.linspace(0, L, nn) bit for bit
-            step = L / (nn - 1)
-            node_positions = np.arange(nn)[None, :] * step[:, None]
-            node_positions[:, -1] = L
-    else:
-        L = np.array([cases[b * C][0] for b in keep_b], np.float64)
-        node_positions = np.stack([np.linspace(0, l_, nn) for l_ in L]) if len(L) else np.zeros((0, nn))
+        col.update(case_cols if (case_cols is not None and all_ok) else case_columns(params, cases, None if all_ok else keep_b))
+        return col
+
+    L = np.array([cases[b * C][0] for b in keep_b], np.float64)
+    node_positions = np.stack([np.linspace(0, l_, nn) for l_ in L]) if len(L) else np.zeros((0, nn))
 
     def ragged(get, dtype, pad):
         rows = [get(i) for i in rec]
@@ -67,46 +125,12 @@ def columnar_from_run(params: BeamOptParams, cases, out: Dict[str, np.ndarray]) 
             lens[i] = len(r)
         return vals, lens
 
-    def ragged_packed(tags, values, dtype, pad):
-        """tags: i32 [records, width0] 1-based, 0 = unused (used slots first); values: same shape or None."""
-        lens = np.count_nonzero(tags, axis=1).astype(np.int32)
-        width = int(lens.max()) if len(lens) else 0
-        src = tags if values is None else values
-        vals = np.where(np.arange(width)[None, :] < lens[:, None], src[:, :width], pad).astype(dtype)
-        return vals, lens
-
-    per_rec_np = rep(node_positions)
-    col = {
-        "I_values": rep(pick_b(out["I"])),
-        "shear_forces": pick_b(out["shear"]).reshape(len(rec), -1),
-        "bending_moments": pick_b(out["moment"]).reshape(len(rec), -1),
-        "rotations": pick_b(out["rot"]).reshape(len(rec), -1),
-        "deflections": pick_b(out["defl"]).reshape(len(rec), -1),
-        "node_positions": per_rec_np,
-        "num_nodes": np.full(len(rec), nn, np.int32),
-        "L": rep(L),
-    }
-    if packed:
-        first = (rec // C) * C                                               # supports shared by the cases of a beam
-        col["roller_nodes"], col["roller_nodes_len"] = ragged_packed(
-            cases.roller_tags if (all_ok and C == 1) else cases.roller_tags[first], None, np.int32, -1)
-        ft = pick_r(cases.force_tags)
-        col["force_nodes"], col["force_nodes_len"] = ragged_packed(ft, None, np.int32, -1)
-        fv = pick_r(cases.force_vals.reshape(len(cases), -1))
-        col["force_values"], col["force_values_len"] = ragged_packed(ft, fv, np.float64, np.nan)
-    else:
-        rollers = lambda i: cases[(i // C) * C][1]                           # noqa: E731  (supports shared by the cases)
-        col["roller_nodes"], col["roller_nodes_len"] = ragged(rollers, np.int32, -1)
-        col["force_nodes"], col["force_nodes_len"] = ragged(lambda i: cases[i][2], np.int32, -1)
-        col["force_values"], col["force_values_len"] = ragged(lambda i: cases[i][3], np.float64, np.nan)
-    rx = np.where(col["roller_nodes"] >= 0, np.take_along_axis(
-        per_rec_np, np.clip(col["roller_nodes"] - 1, 0, nn - 1), axis=1), np.nan) if len(rec) else \
-        np.zeros((0, 0))
-    fx = np.where(col["force_nodes"] >= 0, np.take_along_axis(
-        per_rec_np, np.clip(col["force_nodes"] - 1, 0, nn - 1), axis=1), np.nan) if len(rec) else \
-        np.zeros((0, 0))
-    col["roller_x_locations"], col["roller_x_locations_len"] = rx, col["roller_nodes_len"]
-    col["force_x_locations"], col["force_x_locations_len"] = fx, col["force_nodes_len"]
+    col.update({"node_positions": rep(node_positions), "num_nodes": np.full(len(rec), nn, np.int32), "L": rep(L)})
+    rollers = lambda i: cases[(i // C) * C][1]                               # noqa: E731  (supports shared by the cases)
+    col["roller_nodes"], col["roller_nodes_len"] = ragged(rollers, np.int32, -1)
+    col["force_nodes"], col["force_nodes_len"] = ragged(lambda i: cases[i][2], np.int32, -1)
+    col["force_values"], col["force_values_len"] = ragged(lambda i: cases[i][3], np.float64, np.nan)
+    _x_locations(col, col["node_positions"], nn)
     return col
 
 

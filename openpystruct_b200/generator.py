@@ -301,7 +301,8 @@ def stream_columnar(config: Optional[GeneratorConfig] = None, num_samples: Optio
                     seed: int = 0, device="cuda", reuse_buffers: bool = False):
     """``main()`` of the generators as a PIPELINE (MultiCore:246-262 loops over batches too): yields the columnar record
     arrays of consecutive batches of one seeded stream; the cases of batch i + 1 are drawn (native sampler, its own
-    thread -- ctypes releases the GIL) while the GPU optimises batch i.  The concatenation of the batches is
+    thread -- ctypes releases the GIL -- together with the record keys that depend on the cases alone) while the GPU
+    optimises batch i.  The concatenation of the batches is
     ``generate_columnar(config, num_samples, seed)``.  ``reuse_buffers=True``: the record arrays alias the session's pinned
     host buffers and are valid until the next batch is requested (write them out / consume them first)."""
     from concurrent.futures import ThreadPoolExecutor
@@ -313,20 +314,21 @@ def stream_columnar(config: Optional[GeneratorConfig] = None, num_samples: Optio
     sampler = sampling.NativeSampler(seed)
 
     def draw(count):
-        return sampler.draw_cases(count * p.num_cases, p.num_nodes, cfg.random_bridge, cfg.L_max, rollers, available,
-                                  L_max=cfg.L_max, L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max,
-                                  M_forces_max=cfg.M_forces_max, max_force=cfg.max_force, min_force=cfg.min_force,
-                                  num_cases=p.num_cases, max_forces=p.max_forces)
+        cases = sampler.draw_cases(count * p.num_cases, p.num_nodes, cfg.random_bridge, cfg.L_max, rollers, available,
+                                   L_max=cfg.L_max, L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max,
+                                   M_forces_max=cfg.M_forces_max, max_force=cfg.max_force, min_force=cfg.min_force,
+                                   num_cases=p.num_cases, max_forces=p.max_forces)
+        return cases, _dataset.case_columns(p, cases)              # (the record keys that need no kernel output)
 
     sizes = [min(batch_size, N - s) for s in range(0, N, batch_size)]
     with ThreadPoolExecutor(1) as pool:
         try:
             nxt = pool.submit(draw, sizes[0]) if sizes else None
             for i in range(len(sizes)):
-                cases = nxt.result()
+                cases, case_cols = nxt.result()
                 nxt = pool.submit(draw, sizes[i + 1]) if i + 1 < len(sizes) else None
                 out = optimise_cases(p, cases, device, copy=not reuse_buffers)
-                yield _dataset.columnar_from_run(p, cases, out)
+                yield _dataset.columnar_from_run(p, cases, out, case_cols)
         finally:
             if nxt is not None:
                 nxt.cancel()
