@@ -36,6 +36,32 @@ def test_columnar_equals_the_per_record_dicts(tmp_path):
         assert a == b == got
 
 
+def test_case_columns_computed_ahead_give_the_same_dataset():
+    """stream_columnar computes the record keys that depend on the sampled cases alone on the sampler's thread
+    (dataset.case_columns); the result must be the one-step columnar_from_run, and a batch with a failed beam must fall
+    back to the filtering path."""
+    rollers, avail = sampling.fixed_bridge(101)
+    for num_cases, flag in ((1, 0), (1, 1), (4, 0)):
+        p = BeamOptParams.for_script("MC").replace(num_cases=num_cases, max_e=12)
+        pc = sampling.NativeSampler(17).draw_cases(24 * num_cases, 101, flag, 200.0, rollers, avail, num_cases=num_cases)
+        out = oracle_run(p, *pc.abi_arrays())
+        ahead = dataset.case_columns(p, pc)
+        for drop in (False, True):
+            o = {k: np.array(v) for k, v in out.items()}
+            if drop:
+                o["status"][5] = 1
+            want = dataset.columnar_from_run(p, pc, o)
+            got = dataset.columnar_from_run(p, pc, o, ahead)
+            assert list(want) == list(got)
+            for k in want:
+                assert np.array_equal(want[k], got[k], equal_nan=True), (num_cases, flag, drop, k)
+            assert len(got["L"]) == (24 - drop) * num_cases
+        # and the packed cases produce the records of the per-case tuples
+        listed = dataset.columnar_from_run(p, pc.cases(), out)
+        for k in listed:
+            assert np.array_equal(listed[k], dataset.columnar_from_run(p, pc, out, ahead)[k], equal_nan=True), k
+
+
 def _reference_preprocess(data, n_cases, c, train_split, seed):
     """The trainers' block, restated with the reference's own tools (numpy + sklearn)."""
     def pad(rows):
