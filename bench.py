@@ -294,6 +294,15 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def _launch_plan(p, B):
+    """Kernel family and launch geometry of the timed launch on this device (ops_beamopt_plan)."""
+    from openpystruct_b200 import _cabi
+    try:
+        return _cabi.launch_plan(p, B, 0, 0)
+    except Exception as e:                                  # a diagnostic must not cost the bench line
+        return {"error": str(e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -521,7 +530,7 @@ def run_ours(args):
         "scaling": "strong" if WL.get("shard") else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WL["name"],
                    "beams_per_gpu": B, "num_nodes": NUM_NODES, "num_cases": WL["num_cases"], "epochs": EPOCHS,
-                   "early_stop": False,
+                   "early_stop": False, "launch_plan": _launch_plan(p, B),
                    "fe_precision": "f64", "optimiser_precision": "f32 (torch CPU op order)",
                    "l2": "flushed between steps (256 MiB write)", "collective": "none" if world == 1 else (
                        "dataset gather fused into the kernel: every beam's record is copied to all peers' dataset "

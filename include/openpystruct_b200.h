@@ -241,6 +241,28 @@ void ops_beamopt_session_destroy(OpsBeamOptSession *s);
 int ops_fp64_peak_probe(int iters, double *tflops, float *elapsed_ms, void *cuda_stream);
 
 /*
+ * Diagnostic (no reference counterpart -- the reference has no launch to plan): the kernel family and launch
+ * geometry ops_beamopt_launch would use for a batch of B beams.  Host arithmetic only: with sms > 0 and
+ * smem_optin > 0 (a B200: 148 SMs, 232 448 bytes of opt-in shared memory per CTA) no device is touched, with
+ * 0 / 0 the current device is queried.  Returns 0, OPS_E_BADARG or OPS_E_UNSUPP like the launch would.
+ */
+enum { OPS_PLAN_LANES = 0,               /* eight lanes per beam (x load cases), state in registers */
+       OPS_PLAN_LANES_TM = 1,            /* the same with the lane-private data in tensor memory */
+       OPS_PLAN_WIDE = 2,                /* lanes_per_beam = 8 or 32, state in shared memory (fine discretisations) */
+       OPS_PLAN_THREAD_THREE_MOMENT = 3, /* thread per beam, three-moment solve */
+       OPS_PLAN_THREAD_LDLT = 4 };       /* thread per beam, banded LDL^T */
+typedef struct {
+    int32_t family;
+    int32_t threads, blocks;             /* per CTA; CTAs (persistent: at most one per SM for families 0..2) */
+    int32_t lanes_per_beam;              /* threads working on one beam (all its load cases) */
+    int32_t beams_per_cta;               /* beams resident per CTA and round */
+    int32_t scatter;                     /* 1: ops_beamopt_launch_scatter serves this configuration */
+    int64_t smem_bytes;                  /* dynamic shared memory per CTA */
+    int64_t workspace_bytes;             /* = ops_beamopt_workspace_bytes */
+} OpsLaunchPlanInfo;
+int ops_beamopt_plan(const OpsBeamOptParams *p, int64_t B, int32_t sms, int32_t smem_optin, OpsLaunchPlanInfo *out);
+
+/*
  * Diagnostic (no reference counterpart): sustained issue rate of one instruction class, in warp
  * instructions per clock per SM at the device's maximum clock (8 independent chains per thread,
  * 1024 threads per SM).  op: 0 DFMA, 1 FFMA, 2 FMUL, 3 FADD, 4 MUFU.RCP, 5 F2F (f32<->f64), 6 IMAD,

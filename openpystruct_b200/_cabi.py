@@ -18,6 +18,7 @@ EXPORTS = (
     "ops_fp64_peak_probe", "ops_fastmath_selftest", "ops_pipe_probe",
     "ops_beamopt_session_create", "ops_beamopt_session_arrays", "ops_beamopt_session_run",
     "ops_beamopt_session_destroy",
+    "ops_beamopt_plan",
     "ops_beamopt_launch_scatter", "ops_beamopt_scatter_supported", "ops_peer_alloc", "ops_peer_open", "ops_peer_close", "ops_peer_free",
     "ops_sampler_create", "ops_sampler_destroy", "ops_sampler_random", "ops_sampler_randint", "ops_sampler_draw_cases",
     "ops_frameopt_max_elements", "ops_frameopt_fill_schedule", "ops_frameopt_launch", "ops_frameopt_run_host",
@@ -59,6 +60,16 @@ class OpsBeamOptRecordArrays(C.Structure):
     """One set of dataset arrays (device pointers) of ops_beamopt_launch_scatter."""
     _fields_ = [(n, C.c_void_p) for n in ("I_values", "deflections", "rotations", "shear", "moment", "epochs", "loss",
                                           "status")]
+
+
+class OpsLaunchPlanInfo(C.Structure):
+    _fields_ = [("family", C.c_int32), ("threads", C.c_int32), ("blocks", C.c_int32), ("lanes_per_beam", C.c_int32),
+                ("beams_per_cta", C.c_int32), ("scatter", C.c_int32), ("smem_bytes", C.c_int64),
+                ("workspace_bytes", C.c_int64)]
+
+
+PLAN_FAMILIES = ("lanes", "lanes_tm", "wide", "thread_three_moment", "thread_ldlt")
+B200_SMS, B200_SMEM_OPTIN = 148, 232448
 
 
 class CudaLibraryError(RuntimeError):
@@ -108,6 +119,8 @@ def lib():
         L.ops_beamopt_launch_scatter.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64] + [C.c_void_p] * 5 + \
             [C.c_int, C.POINTER(OpsBeamOptRecordArrays), C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
         L.ops_beamopt_scatter_supported.argtypes = [C.POINTER(OpsBeamOptParams)]
+        L.ops_beamopt_plan.argtypes = [C.POINTER(OpsBeamOptParams), C.c_int64, C.c_int32, C.c_int32,
+                                       C.POINTER(OpsLaunchPlanInfo)]
         L.ops_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
         L.ops_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.ops_peer_close.argtypes = [C.c_void_p]
@@ -174,6 +187,16 @@ def run_host(p: BeamOptParams, fixed_uy, force_nodes, force_vals, L, device: int
         out["loss"].ctypes.data, out["status"].ctypes.data, device, C.byref(ms))
     check(rc, "ops_beamopt_run_host")
     out["kernel_ms"] = float(ms.value)
+    return out
+
+
+def launch_plan(p: BeamOptParams, B: int, sms: int = B200_SMS, smem_optin: int = B200_SMEM_OPTIN) -> dict:
+    """Kernel family and launch geometry ops_beamopt_launch would use for B beams (ops_beamopt_plan: host arithmetic
+    only -- no device is touched unless sms = smem_optin = 0 asks for the current device's figures)."""
+    cp, info = to_c_params(p), OpsLaunchPlanInfo()
+    check(lib().ops_beamopt_plan(C.byref(cp), int(B), int(sms), int(smem_optin), C.byref(info)), "ops_beamopt_plan")
+    out = {name: getattr(info, name) for name, _ in OpsLaunchPlanInfo._fields_}
+    out["family"] = PLAN_FAMILIES[info.family]
     return out
 
 

@@ -441,6 +441,8 @@ static int plan_flex(const BeamConsts &k, int64_t B, int sms, int smem_optin, La
     return 0;
 }
 
+static int plan_launch_on(const BeamConsts &k, int num_cases, int64_t B, int solver, int sms, int smem_optin, LaunchPlan *pl);
+
 static int plan_launch(const BeamConsts &k, int num_cases, int64_t B, int solver, LaunchPlan *pl)
 {
     int dev = 0, sms = 0, smem_optin = 0;
@@ -450,6 +452,12 @@ static int plan_launch(const BeamConsts &k, int num_cases, int64_t B, int solver
     if (e != cudaSuccess) return (int)e;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return (int)e;
+    return plan_launch_on(k, num_cases, B, solver, sms, smem_optin, pl);
+}
+
+// the choice of kernel family and launch geometry: host arithmetic on (parameters, batch size, SM count, shared memory)
+static int plan_launch_on(const BeamConsts &k, int num_cases, int64_t B, int solver, int sms, int smem_optin, LaunchPlan *pl)
+{
     if (solver == OPS_SOLVER_THREE_MOMENT && lanes_supported(k, num_cases)) {
         memset(pl, 0, sizeof *pl);
         pl->lanes = true;
@@ -585,6 +593,38 @@ int ops_beamopt_fill_schedule(const OpsBeamOptParams *p, float *host_table)
         host_table[2 * (t - 1) + 1] = (float)pow(bc2, 0.5);
         lr = lr * p->gamma;
     }
+    return 0;
+}
+
+int ops_beamopt_plan(const OpsBeamOptParams *p, int64_t B, int32_t sms, int32_t smem_optin, OpsLaunchPlanInfo *out)
+{
+    BeamConsts k;
+    if (!p || !out || B < 0) return OPS_E_BADARG;
+    int rc = make_consts(p, &k);
+    if (rc != 0) return rc;
+    LaunchPlan pl;
+    rc = (sms > 0 && smem_optin > 0) ? plan_launch_on(k, p->num_cases, B, p->solver, sms, smem_optin, &pl)
+                                     : plan_launch(k, p->num_cases, B, p->solver, &pl);
+    if (rc != 0) return rc;
+    memset(out, 0, sizeof *out);
+    if (pl.lanes) {
+        out->family = pl.lp.tm ? OPS_PLAN_LANES_TM : OPS_PLAN_LANES;
+        out->threads = pl.lp.threads; out->blocks = pl.lp.blocks; out->smem_bytes = (int64_t)pl.lp.smem_bytes;
+        out->lanes_per_beam = 8 * pl.lp.num_cases;
+        out->beams_per_cta = pl.lp.threads / out->lanes_per_beam;
+        out->scatter = lanes_scatter_supported(pl.lp) ? 1 : 0;
+    } else if (pl.wide) {
+        out->family = OPS_PLAN_WIDE;
+        out->threads = pl.wp.threads; out->blocks = pl.wp.blocks; out->smem_bytes = (int64_t)pl.wp.smem_bytes;
+        out->lanes_per_beam = pl.wp.lpb;
+        out->beams_per_cta = pl.wp.threads / pl.wp.lpb;
+    } else {
+        out->family = pl.flex ? OPS_PLAN_THREAD_THREE_MOMENT : OPS_PLAN_THREAD_LDLT;
+        out->threads = pl.threads; out->blocks = pl.blocks; out->smem_bytes = (int64_t)pl.smem_bytes;
+        out->lanes_per_beam = 1;
+        out->beams_per_cta = pl.threads;
+    }
+    out->workspace_bytes = (int64_t)(256 + pl.ws_d_bytes + pl.ws_f_bytes + pl.ws_mask_bytes + 512);
     return 0;
 }
 

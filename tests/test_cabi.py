@@ -45,6 +45,50 @@ def test_version_and_struct_layout():
     assert C.sizeof(_cabi.OpsBeamOptParams) == C.sizeof(c_oracle.Params)
 
 
+def test_launch_plans_on_a_b200():
+    """ops_beamopt_plan is host arithmetic (148 SMs, 232 448 bytes of opt-in shared memory given: no device touched):
+    which kernel family serves which configuration, and that every plan fits the SM."""
+    p = BeamOptParams.for_script("MC").replace(early_stop=False)
+    smem, sms = _cabi.B200_SMEM_OPTIN, _cabi.B200_SMS
+    # BASELINE configs[1]: two rounds of the 320-thread register instance; one CTA per SM
+    a = _cabi.launch_plan(p, 10000)
+    assert (a["family"], a["threads"], a["blocks"], a["beams_per_cta"], a["scatter"]) == ("lanes", 320, 148, 40, 1)
+    # a fixed-epoch batch that is ONE round of 52..64 beams per SM: the tensor-memory instance, 16 warps
+    b = _cabi.launch_plan(p, 148 * 64)
+    assert (b["family"], b["threads"], b["beams_per_cta"]) == ("lanes_tm", 512, 64)
+    assert _cabi.launch_plan(p.replace(early_stop=True), 148 * 64)["family"] == "lanes"     # ragged stopping: registers
+    # many rounds: twelve warps (three per scheduler)
+    c = _cabi.launch_plan(p, 1000000)
+    assert (c["family"], c["threads"], c["beams_per_cta"]) == ("lanes", 384, 48)
+    # a small batch is spread over as many SMs as it has beams
+    assert _cabi.launch_plan(p, 100)["blocks"] == 100
+    # eight load cases: teams of eight groups (64 threads per beam), five teams per CTA
+    d = _cabi.launch_plan(p.replace(num_cases=8), 100000)
+    assert (d["family"], d["lanes_per_beam"], d["beams_per_cta"], d["scatter"]) == ("lanes", 64, 5, 1)
+    # 1000-element beams: one warp per beam, TWELVE beams per SM (the segment statics live in registers)
+    e = _cabi.launch_plan(p.replace(num_nodes=1001), 100000)
+    assert (e["family"], e["lanes_per_beam"], e["threads"], e["beams_per_cta"], e["scatter"]) == ("wide", 32, 384, 12, 0)
+    # the literal banded LDL^T and the thread-per-beam three-moment kernel behind the same ABI
+    assert _cabi.launch_plan(p.replace(solver=1), 10000)["family"] == "thread_ldlt"
+    assert _cabi.launch_plan(p.replace(solver=2), 10000)["family"] == "thread_three_moment"
+    # every supported discretisation / case count: whole teams per CTA, whole warps, inside the SM's shared memory
+    for nn in (5, 33, 64, 65, 101, 105, 106, 169, 170, 400, 1001, 2001):
+        for nc in (1, 2, 4, 8):
+            q = p.replace(num_nodes=nn, num_cases=nc)
+            if nc > 1 and nn > 105:
+                with pytest.raises(_cabi.CudaLibraryError):
+                    _cabi.launch_plan(q, 5000)
+                continue
+            for B in (1, 37, 5000, 200000):
+                pl = _cabi.launch_plan(q, B)
+                assert pl["smem_bytes"] <= smem and 1 <= pl["blocks"] <= sms, (nn, nc, B, pl)
+                assert pl["threads"] % 32 == 0 and pl["threads"] % pl["lanes_per_beam"] == 0, (nn, nc, B, pl)
+                assert pl["threads"] <= 1024 and pl["beams_per_cta"] >= 1
+                assert pl["family"] == ("wide" if nn > 169 else pl["family"])
+    assert _cabi.launch_plan(p, 10000)["workspace_bytes"] == _cabi.lib().ops_beamopt_workspace_bytes(
+        C.byref(_cabi.to_c_params(p)), 10000) or not torch.cuda.is_available()
+
+
 def test_schedule_is_host_side_and_matches_torch_and_oracle():
     p = BeamOptParams()
     tab = _cabi.fill_schedule(p)
