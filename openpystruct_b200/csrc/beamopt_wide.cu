@@ -32,21 +32,71 @@ __device__ __forceinline__ double group_sum(double v)
 
 // spans whose last element lies in slot s (for any group of the warp): every lane's share, butterfly,
 // lane 0 of the groups concerned publishes the totals
-template <int LPB>
-__device__ __forceinline__ void dev_close(const WideStore &ws, int s, bool cl, const double (&aold)[NSUM], int sold,
-                                          const double (&x)[NSUM], int sp, int l)
+// The five span sums of a whole warp (LPB = 32) with the additions of the butterfly above -- level by level v_l + v_(l ^ step),
+// so the same bits -- but each level done by HALF of the lanes per value (recursive halving): after level 1 the even lanes
+// carry the sums {0, 1, 2} and the odd lanes {3, 4}, after level 3 every lane carries one, 16 shuffles and 8 additions
+// instead of 50 and 25.  The totals end up in lanes 0, 4, 2, 1, 3 (sums 0..4), which store them.
+__device__ __forceinline__ void warp_sum5_store(double (&v)[NSUM], int l, double *tot)
 {
-#pragma unroll 1
-    for (int j = 0; j < NSPAN; ++j) {
-        const bool mine = cl && ws.gi[GI_CLOSE + j] == s;
-        if (!__any_sync(FULL, mine)) continue;
-        double v[NSUM];
-        close_value(aold, sold, x, sp, j, v);
+    static_assert(NSUM == 5, "five sums");
+    const bool b0 = l & 1, b1 = l & 2, b2 = l & 4;
+    // level 1: even lanes keep {0, 1, 2}, odd lanes {3, 4}
+    const double r0 = __shfl_xor_sync(FULL, b0 ? v[0] : v[3], 1);
+    const double r1 = __shfl_xor_sync(FULL, b0 ? v[1] : v[4], 1);
+    const double r2 = __shfl_xor_sync(FULL, v[2], 1);
+    const double a0 = (b0 ? v[3] : v[0]) + r0, a1 = (b0 ? v[4] : v[1]) + r1, a2 = v[2] + r2;      // (a2: even lanes only)
+    // level 2: classes (b0, b1) = (0,0) keep {0, 1}, (0,1) keeps 2, (1,0) keeps 3, (1,1) keeps 4
+    const double other = b0 ? a1 : a2;
+    const double rx = __shfl_xor_sync(FULL, b1 ? a0 : other, 2);
+    const double ry = __shfl_xor_sync(FULL, a1, 2);
+    const double c0 = (b1 ? other : a0) + rx, c1 = a1 + ry;                                        // (c1: class (0,0) only)
+    // level 3: class (0,0) splits {0, 1} over b2, the others go on with their one sum
+    const bool z = !b0 && !b1;
+    const double rz = __shfl_xor_sync(FULL, (z && !b2) ? c1 : c0, 4);
+    double e = ((z && b2) ? c1 : c0) + rz;
+    // levels 4, 5
+    e += __shfl_xor_sync(FULL, e, 8);
+    e += __shfl_xor_sync(FULL, e, 16);
+    if (l < 5) tot[(0x14230u >> (4 * l)) & 7u] = e;               // lanes 0, 1, 2, 3, 4 hold the sums 0, 3, 2, 4, 1
+}
+
+template <int LPB>
+__device__ __forceinline__ void dev_close_span(const WideStore &ws, int j, bool mine, const double (&aold)[NSUM], int sold,
+                                               const double (&x)[NSUM], int sp, int l)
+{
+    double v[NSUM];
+    close_value(aold, sold, x, sp, j, v);
+    if constexpr (LPB == 32) {
+        warp_sum5_store(v, l, ws.tot + j * NSUM);
+    } else {
 #pragma unroll
         for (int w = 0; w < NSUM; ++w) v[w] = group_sum<LPB>(v[w]);
         if (mine && l == 0) {
 #pragma unroll
             for (int w = 0; w < NSUM; ++w) ws.tot[j * NSUM + w] = v[w];
+        }
+    }
+}
+
+template <int LPB>
+__device__ __forceinline__ void dev_close(const WideStore &ws, int s, bool cl, const double (&aold)[NSUM], int sold,
+                                          const double (&x)[NSUM], int sp, int l)
+{
+    if constexpr (LPB == 32) {
+        // one beam per warp: which spans close here is a warp-uniform byte of the beam (no scan over the spans, no votes)
+        unsigned int m = ws.cmask[s];
+#pragma unroll 1
+        while (m) {
+            const int j = __ffs((int)m) - 1;
+            m &= m - 1;
+            dev_close_span<LPB>(ws, j, true, aold, sold, x, sp, l);
+        }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < NSPAN; ++j) {
+            const bool mine = cl && ws.gi[GI_CLOSE + j] == s;
+            if (!__any_sync(FULL, mine)) continue;
+            dev_close_span<LPB>(ws, j, mine, aold, sold, x, sp, l);
         }
     }
 }
@@ -64,7 +114,9 @@ __device__ __forceinline__ void dev_batch(const BeamConsts &k, const FlexBeam &f
         int sold;
         slot_terms<N>(bo, i, x);
         slot_accumulate<LPB>(cx, x, bo.sp[i], aold, sold);
-        if (__any_sync(FULL, bo.close[i])) dev_close<LPB>(ws, kb + i, bo.close[i], aold, sold, x, bo.sp[i], l);
+        // (LPB = 32: the flag is the same on all lanes of the warp -- they belong to one beam)
+        const bool closing = LPB == 32 ? bo.close[i] : (__any_sync(FULL, bo.close[i]) != 0);
+        if (closing) dev_close<LPB>(ws, kb + i, bo.close[i], aold, sold, x, bo.sp[i], l);
     }
 }
 

@@ -74,6 +74,7 @@ struct WideStore {
     float *I0, *m, *v;                          // [K * LPB], element order; I is double-buffered: I0 + (epoch & 1) * el
     int el;                                     // K * LPB
     unsigned char *seg;                         // [K * LPB]: segment id | span id << 4 | (a span closes in this slot) << 7
+    unsigned char *cmask;                       // [K]: bit j = span j closes in this slot (the spans behind bit 7 of seg)
     double *rows;                               // [MAXSEG * row_doubles<LPB>()]
     double *tot;                                // [NSPAN * NSUM] span sums of the inertias about to be analysed
     double *gd;                                 // Moh, Qoh
@@ -125,7 +126,7 @@ OPS_HD size_t wide_beam_bytes(int n)
     size_t b = (size_t)(MAXSEG * row_doubles<LPB>() + NSPAN * NSUM + 2 + FlexStore::NUM_DOUBLES) * 8;   // doubles first
     b += 4 * el * 4;
     b += (size_t)(GI_INTS + FlexStore::NUM_INTS) * 4;
-    b += el;
+    b += el + (size_t)wide_slots<LPB>(n);
     return (b + 15) / 16 * 16;
 }
 template <int LPB>
@@ -147,6 +148,7 @@ OPS_HD void wide_carve(unsigned char *base, int n, WideStore &ws)
     ws.fs.si = i; i += FlexStore::NUM_INTS;
     ws.fs.stride = 1;
     ws.seg = reinterpret_cast<unsigned char *>(i);
+    ws.cmask = ws.seg + el;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -163,6 +165,7 @@ OPS_HD int wide_setup(const BeamConsts &k, double L, FixedFn fixed, const int *f
     ws.gd[0] = fb.Moh; ws.gd[1] = fb.Qoh;
     for (int i = 0; i < NSPAN * NSUM; ++i) ws.tot[i] = 0.0;
     for (int j = 0; j < NSPAN; ++j) ws.gi[GI_CLOSE + j] = -1;
+    for (int s_ = 0; s_ < wide_slots<LPB>(k.n); ++s_) ws.cmask[s_] = 0;
     int ns = 0;
     if (rc == 0) {
         const int n = k.n, m = fb.m, last = fb.last, nl = fb.nloads;
@@ -189,6 +192,7 @@ OPS_HD int wide_setup(const BeamConsts &k, double L, FixedFn fixed, const int *f
             const int na = ws.fs.sup(j - 1), nb = ws.fs.sup(j);
             const double ra = ws.fs.span(j, FlexStore::RA);
             ws.gi[GI_CLOSE + j - 1] = (nb - 1) / LPB;
+            ws.cmask[(nb - 1) / LPB] |= (unsigned char)(1u << (j - 1));
             double SP = 0.0, D = 0.0;                    // sum P, sum P (na - nd) over the loads left of the segment
             emit(na, j - 1, na, 0.0, Le * ra, ra);
             while (li < nl && ws.fs.lnode(li) < nb) {
@@ -494,6 +498,17 @@ OPS_HD void sweep_batch(const BeamConsts &k, const FlexBeam &fb, const WideShape
         } else {
             loss_grad_batch<N>(k, I, c, h, d, q, g);
         }
+        // torch.sum partials.  LPB = 32, the batch inside the whole 32-blocks and inside one 16-block cascade chunk (all
+        // but the last batch of a sweep): one accumulator per quantity, one test per batch instead of three per slot
+        const bool plain = LPB == 32 && kb + N <= sh.blk && (kb & 15) + N <= 16;
+        if (plain) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { cx.acc[0][0] += I[i]; cx.acc[1][0] += d[i]; cx.acc[2][0] += q[i]; }
+            if (kb + N <= sh.casc_slots && ((kb + N) & 15) == 0) {                   // a 16-block chunk is complete
+#pragma unroll
+                for (int w = 0; w < 3; ++w) { cx.lv[w] += cx.acc[w][0]; cx.acc[w][0] = 0.0f; }
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int s = kb + i;
@@ -509,6 +524,7 @@ OPS_HD void sweep_batch(const BeamConsts &k, const FlexBeam &fb, const WideShape
 #pragma unroll
                 for (int w = 0; w < 3; ++w) { cx.lv[w] += cx.acc[w][0]; cx.acc[w][0] = 0.0f; }
             }
+        }
         }
         if constexpr (N % 2 == 0) {
             fm::F2 Ip[N / 2], mp[N / 2], vp[N / 2], gp[N / 2];
