@@ -108,6 +108,19 @@ __device__ __forceinline__ void dev_batch(const BeamConsts &k, const FlexBeam &f
 {
     BatchOut<N> bo;
     sweep_batch<LPB, N>(k, fb, sh, ws, l, kb, run, Icur, Inew, sc, cx, bo);
+    if constexpr (LPB == 32 && N == 4) {
+        // most batches close no span: one test of the batch's four bytes (kb is a multiple of four), then no branches
+        if (*reinterpret_cast<const unsigned int *>(ws.cmask + kb) == 0u) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double x[NSUM], aold[NSUM];
+                int sold;
+                slot_terms<N>(bo, i, x);
+                slot_accumulate<LPB>(cx, x, bo.sp[i], aold, sold);
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double x[NSUM], aold[NSUM];
