@@ -30,8 +30,6 @@ __device__ __forceinline__ double group_sum(double v)
     return v;
 }
 
-// spans whose last element lies in slot s (for any group of the warp): every lane's share, butterfly,
-// lane 0 of the groups concerned publishes the totals
 // The five span sums of a whole warp (LPB = 32) with the additions of the butterfly above -- level by level v_l + v_(l ^ step),
 // so the same bits -- but each level done by HALF of the lanes per value (recursive halving): after level 1 the even lanes
 // carry the sums {0, 1, 2} and the odd lanes {3, 4}, after level 3 every lane carries one, 16 shuffles and 8 additions
@@ -60,6 +58,7 @@ __device__ __forceinline__ void warp_sum5_store(double (&v)[NSUM], int l, double
     if (l < 5) tot[(0x14230u >> (4 * l)) & 7u] = e;               // lanes 0, 1, 2, 3, 4 hold the sums 0, 3, 2, 4, 1
 }
 
+// span j closes in this slot
 template <int LPB>
 __device__ __forceinline__ void dev_close_span(const WideStore &ws, int j, bool mine, const double (&aold)[NSUM], int sold,
                                                const double (&x)[NSUM], int sp, int l)
@@ -78,6 +77,8 @@ __device__ __forceinline__ void dev_close_span(const WideStore &ws, int j, bool 
     }
 }
 
+// spans whose last element lies in slot s (for any group of the warp): every lane's share of the span's five sums,
+// added across the group in the butterfly's order, published in the beam's `tot`
 template <int LPB>
 __device__ __forceinline__ void dev_close(const WideStore &ws, int s, bool cl, const double (&aold)[NSUM], int sold,
                                           const double (&x)[NSUM], int sp, int l)
