@@ -31,7 +31,9 @@
 //
 // Span sums: a lane keeps five running sums for the span its slots are in; when a span's last element
 // falls into slot k (a group-uniform event), every lane contributes its sums of that span and the group
-// adds them with a fixed butterfly (deterministic; all lanes obtain the same bits).  No per-lane scratch.
+// adds them in the order of a fixed butterfly (deterministic).  No per-lane scratch.  Which spans close in a
+// slot is one byte per slot (`cmask`, written at set-up): the 32-lane kernel tests a batch's four bytes at once
+// and walks the set bits, so a sweep has no scan over the spans and no warp votes (beamopt_wide.cu).
 //
 // The functions here contain no CUDA intrinsics: the two cross-lane steps (butterfly sum, final loss
 // combine) are done by the caller -- shuffles in beamopt_wide.cu, arrays in tests/hostsim.
