@@ -293,6 +293,12 @@ def generate_columnar(config: Optional[GeneratorConfig] = None, num_samples: Opt
                                       L_min=cfg.L_min, N_rollers_max=cfg.N_rollers_max, M_forces_max=cfg.M_forces_max,
                                       max_force=cfg.max_force, min_force=cfg.min_force, rng=rng)
                  for _ in range(N * p.num_cases)]
+    if isinstance(cases, sampling.PackedCases):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(1) as pool:                    # the record keys that need no kernel output, beside the GPU run
+            ahead = pool.submit(_dataset.case_columns, p, cases)
+            out = optimise_cases(p, cases, device)
+            return _dataset.columnar_from_run(p, cases, out, ahead.result())
     out = optimise_cases(p, cases, device)
     return _dataset.columnar_from_run(p, cases, out)
 
